@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — views/sec of the Latent-Paint render path (forward + backward), BASELINE.json's metric.
+
+Workload (``config.workload``): BASELINE.json configs[1] — shapes/nascar.obj (V=3750, F=7500,
+deterministic grid-atlas UVs), 3-channel 1024² RGB texture, 512×512 render, batch of
+8 random views per GPU, latent_paint flavour, bilinear.  One *step* = one forward render of the 8
+views + one backward scatter of a dense upstream gradient into the texture gradient (+ one NCCL
+all-reduce of that gradient when N > 1: views shard over ranks, weak scaling).
+
+  value      device-timed views/s, inputs resident in HBM, steps replayed from CUDA graphs
+  e2e        same metric through lp_render_step_host with pinned HOST buffers (H2D + D2H inside)
+  roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration (an
+             instrumented eager pass over the same steps) against MEASURED_PEAKS.json HBM GB/s
+  cpu_baseline  the oracle (reference glue mirror over the torch kaolin restatement) on the host cores
+
+``--impl reference`` times that CPU path alone and prints the same line with "impl": "reference".
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import latent_nerf_test_b200 as lp  # noqa: E402
+from latent_nerf_test_b200 import _lib  # noqa: E402
+
+WORKLOADS = {
+    # name: shape, scale, dy, H, W, C, T, views per GPU, interpolation
+    "c2": dict(shape="nascar", scale=0.6, dy=0.25, H=512, W=512, C=3, T=1024, B=8, interp="bilinear",
+               label="configs[1]: nascar.obj F=7500, 3ch 1024^2 texture, 512x512, 8 views/GPU, latent_paint flavour, bilinear"),
+    "c1": dict(shape="blub", scale=0.6, dy=0.25, H=64, W=64, C=4, T=128, B=1, interp="nearest",
+               label="configs[0]: blub.obj F=14208, 4ch 128^2 latent texture, 64x64, 1 view, nearest"),
+}
+FOV = np.pi / 3
+
+
+def algorithmic_bytes(V, F, H, W, C, T, B):
+    """SURVEY.md §8(d) / BASELINE.md §3, split per kernel (DESIGN.md 'Algorithmic bytes')."""
+    fwd = B * (12 * V + 36 * F + H * W * (4 * C + 12)) + 4 * C * T * T
+    bwd = B * (H * W * (4 * C + 8)) + 4 * C * T * T
+    return fwd, bwd
+
+
+def make_views(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    radius = torch.rand(B, generator=g) * 0.5 + 1.0
+    theta = torch.deg2rad(torch.rand(B, generator=g) * 135.0 + 15.0)
+    phi = torch.deg2rad(torch.rand(B, generator=g) * 360.0)
+    return radius, theta, phi
+
+
+def cameras_for(radius, theta, phi, dy):
+    return torch.cat([lp.camera.camera_from_view(theta[i], phi[i], float(radius[i]), dy) for i in range(len(theta))]).contiguous()
+
+
+def load_scene(w):
+    m = lp.meshio.find_shape(w["shape"])
+    verts = lp.meshio.normalize_vertices(m.vertices, w["scale"], w["dy"])
+    return verts, m.faces, lp.meshio.face_uv_attributes(m)
+
+
+class DeviceStep:
+    """One buffer set + the two C-ABI argument blocks of a fwd+bwd step on resident inputs."""
+
+    def __init__(self, geom, w, cams, seed, device):
+        verts, faces, uv = geom
+        B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
+        self.device = device
+        self.tex = (0.4 * torch.randn(1, C, T, T, generator=torch.Generator().manual_seed(seed))).to(device)
+        self.grad_image = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(seed + 1)).to(device)
+        self.cams = cams.to(device)
+        self.image = torch.empty(B, C, H, W, device=device)
+        self.mask = torch.empty(B, 1, H, W, device=device)
+        self.uv = torch.empty(B, H, W, 2, device=device)
+        self.grad_tex = torch.zeros(C, T, T, device=device)
+        L = _lib.lib()
+        self.ws = torch.empty(int(L.lp_workspace_bytes(B, faces.shape[0], H, W)), dtype=torch.uint8, device=device)
+        a = _lib.LpForwardArgs()
+        a.verts, a.faces, a.V, a.F = verts.data_ptr(), faces.data_ptr(), verts.shape[0], faces.shape[0]
+        a.cameras, a.B, a.H, a.W = self.cams.data_ptr(), B, H, W
+        p = 1.0 / np.tan(FOV / 2)
+        a.proj[0], a.proj[1], a.proj[2] = p, p, -1.0
+        a.multiplier, a.eps = 1000.0, 1e-8
+        a.flags = _lib.LP_FLAG_MASK_IMAGE | _lib.LP_FLAG_REJECT_BEHIND
+        a.face_uv, a.texture = uv.data_ptr(), self.tex.data_ptr()
+        a.C, a.Th, a.Tw = C, T, T
+        a.interp = _lib.LP_INTERP_BILINEAR if w["interp"] == "bilinear" else _lib.LP_INTERP_NEAREST
+        a.image, a.mask, a.uv = self.image.data_ptr(), self.mask.data_ptr(), self.uv.data_ptr()
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        b = _lib.LpBackwardArgs()
+        b.B, b.H, b.W, b.flags = B, H, W, a.flags
+        b.grad_image, b.uv = self.grad_image.data_ptr(), self.uv.data_ptr()
+        b.C, b.Th, b.Tw, b.interp = C, T, T, a.interp
+        b.grad_texture = self.grad_tex.data_ptr()
+        self.fwd, self.bwd = a, b
+        self.keep = (verts, faces, uv)
+        self.launches = 0
+
+    def run(self):
+        """Enqueue forward, zero the gradient, backward on torch's current stream."""
+        L = _lib.lib()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(L.lp_render_forward(ctypes.byref(self.fwd), stream))
+        n = L.lp_last_launch_count()
+        self.grad_tex.zero_()
+        _lib.check(L.lp_render_backward(ctypes.byref(self.bwd), stream))
+        self.launches = n + L.lp_last_launch_count()
+
+
+class HostStep:
+    """The reference-facing call with HOST buffers: pinned cameras / upstream gradient in, pinned
+    image / mask / texture gradient out, through ``lp_render_step_host`` (tests use it too)."""
+
+    def __init__(self, verts, faces, uv, texture, B, H, W, interp, fov, device="cuda:0"):
+        self.device = torch.device(device)
+        geom = (verts.to(self.device).float().contiguous(), faces.to(self.device, torch.int32).contiguous(),
+                uv.to(self.device).float().reshape(-1, 3, 2).contiguous())
+        C, T = texture.shape[1], texture.shape[-1]
+        w = dict(B=B, H=H, W=W, C=C, T=T, interp=interp)
+        self.dev = DeviceStep(geom, w, torch.zeros(B, 4, 3), 0, self.device)
+        self.dev.tex.copy_(texture.reshape(1, C, T, T))
+        self.h_cams = torch.empty(B, 4, 3).pin_memory()
+        self.h_grad = torch.empty(B, C, H, W).pin_memory()
+        self.h_image = torch.empty(B, C, H, W).pin_memory()
+        self.h_mask = torch.empty(B, 1, H, W).pin_memory()
+        self.h_gtex = torch.empty(C, T, T).pin_memory()
+        self.h2d_bytes = self.h_cams.numel() * 4 + self.h_grad.numel() * 4
+        self.d2h_bytes = (self.h_image.numel() + self.h_mask.numel() + self.h_gtex.numel()) * 4
+
+    def step(self, cams=None, grad_image=None):
+        if cams is not None:
+            self.h_cams.copy_(cams)
+        if grad_image is not None:
+            self.h_grad.copy_(grad_image)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().lp_render_step_host(
+                ctypes.byref(self.dev.fwd), ctypes.byref(self.dev.bwd), self.h_cams.data_ptr(), self.h_grad.data_ptr(),
+                self.h_image.data_ptr(), self.h_mask.data_ptr(), self.h_gtex.data_ptr(), stream))
+        return self.h_image, self.h_mask, self.h_gtex
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_views_per_s(w, n_views, seed=0, warmup=0, impl="torch"):
+    """The oracle port of the reference CPU path: reference glue mirror over the torch kaolin
+    restatement (rasterizer in torch, all host threads), forward + backward, one view per call as
+    in the reference's latent_paint Renderer."""
+    from oracle import kaolin_shim, renderer_ref
+    kaolin_shim.RASTER_IMPL = impl
+    torch.set_num_threads(os.cpu_count() or 1)
+    verts, faces, uv = load_scene(w)
+    tex = (0.4 * torch.randn(1, w["C"], w["T"], w["T"], generator=torch.Generator().manual_seed(seed))).requires_grad_(True)
+    grad = torch.randn(1, w["C"], w["H"], w["W"], generator=torch.Generator().manual_seed(seed + 1))
+    radius, theta, phi = make_views(warmup + n_views, seed)
+    r = renderer_ref.LatentPaintRendererRef(dim=(w["W"], w["H"]), interpolation_mode=w["interp"])
+    t0 = None
+    for i in range(warmup + n_views):
+        if i == warmup:
+            t0 = time.perf_counter()
+        tex.grad = None
+        image, _ = r.render_single_view_texture(verts, faces, uv, tex, elev=float(theta[i]), azim=float(phi[i]),
+                                                radius=float(radius[i]), look_at_height=w["dy"])
+        image.backward(grad)
+    dt = time.perf_counter() - t0
+    return n_views / dt, dt
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = w["B"]
+    # each step = one batch of B views on the CPU (≈0.2 s/view on 8 cores for c2)
+    total = (args.warmup + args.steps) * B
+    cap = 400                                        # bound the run to a few minutes
+    per_step = B if total <= cap else max(1, cap // (args.warmup + args.steps))
+    vps, dt = cpu_reference_views_per_s(w, args.steps * per_step, warmup=args.warmup * per_step)
+    line = {"metric": "views/sec (fwd+bwd render)", "value": vps, "unit": "views/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "views_per_step": per_step},
+            "cpu_baseline": {"value": vps, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.steps} steps x {per_step} views, torch CPU path of the oracle "
+                                       f"(reference render.py mirror over the torch kaolin restatement)"},
+            "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-views", type=int, default=40, help="views timed for cpu_baseline (0 = skip)")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU implementation (use --impl reference)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    verts, faces, uv = load_scene(w)
+    geom = (verts.to(device).float().contiguous(), faces.to(device, torch.int32).contiguous(),
+            uv.to(device).float().reshape(-1, 3, 2).contiguous())
+    B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
+    V, F = verts.shape[0], faces.shape[0]
+    sets = []
+    for s in range(args.sets):
+        radius, theta, phi = make_views(B, 1000 * rank + s)
+        sets.append(DeviceStep(geom, w, cameras_for(radius, theta, phi, w["dy"]), 10 * s + 1, device))
+    set_bytes = sum(t.numel() * t.element_size() for t in (sets[0].tex, sets[0].grad_image, sets[0].image, sets[0].mask,
+                                                           sets[0].uv, sets[0].grad_tex))
+
+    stream = torch.cuda.Stream(device)
+    graphs = None
+    with torch.cuda.stream(stream):
+        for s in sets:                                   # first touch + correctness of the call chain
+            s.run()
+        stream.synchronize()
+        if not args.no_graph:
+            try:
+                graphs = []
+                for s in sets:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream):
+                        s.run()
+                    graphs.append(g)
+            except Exception as exc:                      # eager launches still measure the same kernels
+                print(f"bench.py: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+                graphs = None
+    launches_per_step = sets[0].launches
+
+    def one_step(i):
+        k = i % len(sets)
+        if graphs is not None:
+            graphs[k].replay()
+        else:
+            sets[k].run()
+        if world > 1:
+            dist.all_reduce(sets[k].grad_tex)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            one_step(i)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            one_step(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # keep the GPU busy a little longer if the region was too short for nvidia-smi to sample it
+        if sampler and ms < 400:
+            t_end = time.time() + 0.5
+            while time.time() < t_end:
+                for i in range(50):
+                    one_step(i)
+                torch.cuda.synchronize(device)
+        clocks = sampler.summary() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- roofline: instrumented eager pass over the same steps (events around every kernel)
+        L = _lib.lib()
+        with torch.cuda.stream(stream):
+            L.lp_timing_enable(1)
+            n_prof = min(args.steps, 200)
+            for i in range(n_prof):
+                sets[i % len(sets)].run()
+            torch.cuda.synchronize(device)
+            timings = _lib.collect_timings()
+            L.lp_timing_enable(0)
+        per_kernel = {k: 1e3 * v[0] / v[1] for k, v in timings.items()}           # µs per launch
+        fwd_bytes, bwd_bytes = algorithmic_bytes(V, F, H, W, C, T, B)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        kb = {"k_raster_shade": fwd_bytes, "k_backward_texture": bwd_bytes}
+        dom = max(kb, key=lambda k: per_kernel.get(k, 0.0))
+        achieved = kb[dom] / (per_kernel[dom] * 1e-6) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")                       # dram bytes per launch from ncu --set full
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kb[dom], "us_per_launch": per_kernel[dom],
+                    "kernels_us": per_kernel,
+                    "step": {"algorithmic_bytes": fwd_bytes + bwd_bytes,
+                             "achieved_gbs": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9,
+                             "frac": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9 / peak}}
+
+        # ---- e2e: host buffers through lp_render_step_host
+        hs = HostStep(verts, faces, uv, sets[0].tex.cpu(), B, H, W, w["interp"], FOV, device=str(device))
+        radius, theta, phi = make_views(B, 77)
+        hs.h_cams.copy_(cameras_for(radius, theta, phi, w["dy"]))
+        hs.h_grad.copy_(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5)))
+        n_e2e = max(5, min(args.steps, 50))
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                hs.step()
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                hs.step()
+            torch.cuda.synchronize(device)
+            e2e_s = time.perf_counter() - t0
+        e2e = {"value": B * n_e2e / e2e_s, "unit": "views/s", "h2d_bytes_per_step": hs.h2d_bytes,
+               "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": 1e3 * e2e_s / n_e2e, "n_gpus": 1}
+
+        # ---- cpu baseline: bounded sample of the same workload on the host cores
+        cpu = None
+        if args.cpu_views > 0 and world == 1:
+            vps, dt = cpu_reference_views_per_s(w, args.cpu_views, warmup=2)
+            cpu = {"value": vps, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{args.cpu_views} views of the same workload, one view per call, {dt:.1f} s; oracle torch CPU path"}
+
+        line = {"metric": "views/sec (fwd+bwd render)", "value": value, "unit": "views/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["label"], "views_per_gpu_per_step": B, "cuda_graph": graphs is not None,
+                           "l2": f"{len(sets)} rotating buffer sets of {set_bytes / 1e6:.0f} MB each "
+                                 f"({len(sets) * set_bytes / 1e6:.0f} MB > 126 MB L2): inputs larger than L2",
+                           "parallelism": f"views sharded over {world} GPU(s)" + (", NCCL all-reduce of the texture gradient each step" if world > 1 else "")},
+                "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/*
+ * lp_b200 — C ABI of the B200-native Latent-Paint mesh renderer (sm_100a).
+ *
+ * Drop-in boundary: these entry points are what the reference's renderer would bind in place
+ * of the kaolin / ATen calls on its render path.  Each one names the reference interface it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   lp_cameras_from_views   Renderer.get_camera_from_view            src/latent_paint/models/render.py:19-31
+ *                                                                    src/latent_paint_mesh/models/render.py:42-55
+ *                           (+ kal.render.camera.generate_transformation_matrix)
+ *   lp_render_forward       kal.render.mesh.prepare_vertices         src/latent_paint/models/render.py:39,56
+ *                           kal.render.mesh.rasterize                src/latent_paint/models/render.py:42,59
+ *                           kal.render.mesh.dibr_rasterization       src/latent_paint_mesh/models/render.py:231
+ *                           kal.render.mesh.texture_mapping          src/latent_paint/models/render.py:64
+ *                                                                    src/latent_paint_mesh/models/render.py:243
+ *                           mask / white background composition      src/latent_paint/models/render.py:45,63-67
+ *                           kal.render.mesh.spherical_harmonic_lighting  src/latent_paint_mesh/models/render.py:258-259
+ *   lp_vertex_normals       Renderer.compute_vertex_normals          src/latent_paint_mesh/models/render.py:57-105
+ *                           (+ kal.ops.mesh.index_vertices_by_faces, :202 — gathered inside lp_render_forward)
+ *   lp_render_backward      autograd backward of grid_sample (texture_mapping) and of kaolin's rasterize
+ *                           into the face features: pred.backward(gradient=grad)
+ *                                                                    src/latent_paint_mesh/training/trainer.py:656-660
+ *   lp_render_step_host     one forward+backward through host buffers (what bench.py's e2e times)
+ *
+ * Conventions: every pointer is caller-owned; device pointers unless the name ends in _host.
+ * All floating point is fp32, indices int32.  Calls only enqueue work on the given stream
+ * (a cudaStream_t passed as void*); they never synchronise the device (lp_render_step_host
+ * excepted) and allocate nothing.  Return value: LP_OK or an LP_ERR_* code;
+ * lp_last_error() gives the message of the last failure on the calling thread.
+ */
+#ifndef LP_B200_H
+#define LP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LP_B200_VERSION 100
+
+enum {
+    LP_OK = 0,
+    LP_ERR_BAD_ARG = 1,      /* null pointer, non-positive size, inconsistent shapes */
+    LP_ERR_UNSUPPORTED = 2,  /* e.g. bicubic interpolation, too many channels */
+    LP_ERR_WORKSPACE = 3,    /* workspace missing or smaller than lp_workspace_bytes() */
+    LP_ERR_CUDA = 4          /* a CUDA runtime call failed; see lp_last_error() */
+};
+
+enum { LP_INTERP_NEAREST = 0, LP_INTERP_BILINEAR = 1 };
+
+/* LpForwardArgs.flags / LpBackwardArgs.flags */
+enum {
+    LP_FLAG_MASK_IMAGE       = 1u << 0, /* image *= (face_idx > -1); mask output is that 0/1 mask
+                                           (latent_paint flavour, render.py:63-65).  Without it the
+                                           image is not masked and the mask output is the interpolated
+                                           all-ones feature (latent_paint_mesh flavour, render.py:224-243) */
+    LP_FLAG_WHITE_BACKGROUND = 1u << 1, /* image += 1 * (1 - mask) */
+    LP_FLAG_REJECT_BEHIND    = 1u << 2, /* faces whose interpolated depth is not < 0 never win (BASELINE.md decree 3) */
+    LP_FLAG_CULL_NZ_ZERO     = 1u << 3, /* drop faces whose unit camera-space normal has |n_z| == 0:
+                                           dibr_rasterization's valid_faces as the reference calls it with abs() */
+    LP_FLAG_SHADE_FEATURES   = 1u << 4  /* interpolate face_features instead of sampling a texture
+                                           (Renderer.render_single_view, latent_paint render.py:34-47) */
+};
+
+typedef struct LpForwardArgs {
+    /* geometry — prepare_vertices inputs */
+    const float   *verts;          /* (V,3) */
+    const int32_t *faces;          /* (F,3) */
+    int32_t        V, F;
+    /* views */
+    const float   *cameras;        /* (B,4,3) look-at matrices [R;t]: v_cam = [v,1] @ M */
+    int32_t        B;
+    float          proj[3];        /* camera_proj vector: (1/tan(fov/2), 1/tan(fov/2), -1) */
+    int32_t        H, W;           /* output rows, columns  (the reference passes dims[1], dims[0]) */
+    float          multiplier;     /* kaolin rasterize multiplier (1000) */
+    float          eps;            /* kaolin rasterize eps (1e-8) */
+    uint32_t       flags;
+    /* texture shading (flags without LP_FLAG_SHADE_FEATURES) */
+    const float   *face_uv;        /* (F,3,2) per-face-corner UVs, shared by all views */
+    const float   *texture;        /* (C,Th,Tw) planar, the reference's (1,C,T,T) parameter */
+    int32_t        C, Th, Tw;
+    int32_t        interp;         /* LP_INTERP_* */
+    /* face-feature shading (LP_FLAG_SHADE_FEATURES) */
+    const float   *face_features;  /* (Bf,F,3,D) with Bf = 1 or B */
+    int32_t        D, features_batched;
+    /* latent_paint_mesh extras: needed only when the normals / lighting outputs are requested.
+       The call then also runs the lp_vertex_normals step between face setup and shading. */
+    const int32_t *vf_offsets;     /* (V+1) vertex -> incident-corner CSR, see lp_vertex_normals */
+    const int32_t *vf_faces;       /* (3F) */
+    float         *face_normals;   /* out/scratch (B,F,3): unit camera-space face normals */
+    float         *vertex_normals; /* out/scratch (B,V,3): averaged, not re-normalised */
+    const float   *lights;         /* (9) SH coefficients */
+    /* outputs; image and mask are required, the rest may be NULL */
+    float         *image;          /* (B,C|D,H,W) */
+    float         *mask;           /* (B,1,H,W) */
+    float         *uv;             /* (B,H,W,2) interpolated UVs, saved for lp_render_backward;
+                                      with LP_FLAG_MASK_IMAGE uncovered pixels hold u = -1 */
+    int32_t       *face_idx;       /* (B,H,W) winning face, -1 = none */
+    float         *bary;           /* (B,H,W,3) perspective-correct weights w' */
+    float         *depth;          /* (B,H,W) camera-space z of the visible surface, 0 = none */
+    float         *normals;        /* (B,3,H,W) interpolated averaged vertex normals */
+    float         *lighting;       /* (B,1,H,W) clamp(SH(normals)·lights, 1e-8, 1) */
+    /* scratch */
+    void          *workspace;
+    uint64_t       workspace_bytes;
+} LpForwardArgs;
+
+typedef struct LpBackwardArgs {
+    int32_t        B, H, W;
+    uint32_t       flags;          /* same flags as the forward call */
+    const float   *grad_image;     /* (B,C|D,H,W) dL/d image */
+    /* texture path */
+    const float   *uv;             /* (B,H,W,2) saved by the forward */
+    int32_t        C, Th, Tw, interp;
+    float         *grad_texture;   /* (C,Th,Tw) planar; ACCUMULATED into (caller zeroes it) */
+    /* face-feature path */
+    const int32_t *face_idx;       /* (B,H,W) */
+    const float   *bary;           /* (B,H,W,3) */
+    int32_t        F, D, features_batched;
+    float         *grad_face_features; /* (Bf,F,3,D); ACCUMULATED into */
+} LpBackwardArgs;
+
+int         lp_version(void);
+const char *lp_last_error(void);
+const char *lp_error_string(int code);
+
+/* bytes of device scratch lp_render_forward needs for B views of F faces at H x W */
+uint64_t    lp_workspace_bytes(int32_t B, int32_t F, int32_t H, int32_t W);
+
+/* elev/azim/radius: (B) device arrays (radius_stride 0 broadcasts one value); cameras out (B,4,3) */
+int lp_cameras_from_views(const float *elev, const float *azim, const float *radius, int32_t radius_stride,
+                          float look_at_height, int32_t B, float *cameras, void *stream);
+
+int lp_render_forward(const LpForwardArgs *args, void *stream);
+int lp_render_backward(const LpBackwardArgs *args, void *stream);
+
+/* vertex → incident (corner-major, face-ascending) CSR: offsets (V+1), entries (3F) hold face ids.
+ * face_normals (B,F,3) → vertex_normals (B,V,3) = mean of incident unit face normals, not re-normalised */
+int lp_vertex_normals(const float *face_normals, const int32_t *vf_offsets, const int32_t *vf_faces,
+                      int32_t B, int32_t V, int32_t F, float *vertex_normals, void *stream);
+
+/* One latent_paint-flavour forward + backward through HOST buffers: copies cameras and grad_image
+ * host→device, renders, scatters the gradient, copies image, mask and grad_texture device→host and
+ * synchronises the stream.  Geometry, texture and all device scratch are caller-provided device
+ * memory referenced by `fwd` / `bwd` (their image/mask/uv/grad pointers are device staging). */
+int lp_render_step_host(const LpForwardArgs *fwd, const LpBackwardArgs *bwd,
+                        const float *cameras_host, const float *grad_image_host,
+                        float *image_host, float *mask_host, float *grad_texture_host, void *stream);
+
+/* Instrumentation (bench.py's roofline leg): while enabled, every kernel launch of this library is
+ * bracketed by CUDA events on its stream.  lp_timing_collect waits for them, sums the elapsed
+ * milliseconds per kernel name into total_ms[]/counts[] (names[] receives static strings), clears
+ * the record and returns the number of distinct names, or -LP_ERR_CUDA.  Not
+ * usable during stream capture. */
+int lp_timing_enable(int on);
+int lp_timing_collect(int max_names, const char **names, float *total_ms, int *counts);
+
+/* number of kernel launches the last lp_render_forward / lp_render_backward on this thread enqueued */
+int lp_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LP_B200_H */

@@ -1,0 +1,272 @@
+"""Autograd-connected calls into the C ABI (``include/lp_b200.h``).
+
+``render_texture`` stands where the reference chains ``prepare_vertices → rasterize /
+dibr_rasterization → texture_mapping → mask composition`` (reference
+``src/latent_paint/models/render.py:56-67``, ``src/latent_paint_mesh/models/render.py:194-277``);
+``render_face_features`` where it rasterizes per-face-vertex colours (``render.py:39-45``).
+Only the texture / the face features receive gradients, exactly as in the reference (UVs are
+detached there, ``render.py:61``; vertices never require grad).
+
+torch provides device memory and the stream; every kernel is ours.  No CPU fallback: a CPU
+tensor for the texture or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from ._lib import LpBackwardArgs, LpForwardArgs
+
+_INTERP = {"nearest": _lib.LP_INTERP_NEAREST, "bilinear": _lib.LP_INTERP_BILINEAR}
+
+#: kernel launches enqueued by this process through the wrappers below (bench.py reads it)
+launch_counter = {"kernels": 0}
+
+_workspaces: dict = {}
+_int32_cache: dict = {}
+_csr_cache: dict = {}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"lp_b200: '{name}' must be a CUDA tensor — this renderer has no CPU path")
+
+
+def _workspace(device, nbytes):
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _faces_i32(faces, device):
+    """The reference carries faces as int64 (LongTensor); the kernels read int32.  Converted
+    once per (tensor, version)."""
+    if faces.dtype == torch.int32 and faces.device == device and faces.is_contiguous():
+        return faces
+    key = (faces.data_ptr(), faces._version, tuple(faces.shape), faces.dtype, str(device))
+    hit = _int32_cache.get(key)
+    if hit is None:
+        if len(_int32_cache) > 16:
+            _int32_cache.clear()
+        hit = faces.detach().to(device=device, dtype=torch.int32).contiguous()
+        _int32_cache[key] = hit
+    return hit
+
+
+def vertex_face_csr(faces_i32, num_vertices):
+    """Vertex → incident-corner lists in the order the reference accumulates them in
+    ``compute_vertex_normals`` (render.py:99-101): corner 0 of every face in face order, then
+    corner 1, then corner 2.  One stable sort per mesh topology, cached."""
+    key = (faces_i32.data_ptr(), faces_i32._version, tuple(faces_i32.shape), num_vertices)
+    hit = _csr_cache.get(key)
+    if hit is None:
+        if len(_csr_cache) > 16:
+            _csr_cache.clear()
+        F = faces_i32.shape[0]
+        corner_major = faces_i32.t().reshape(-1).long()                    # (3F): k*F + f
+        order = torch.sort(corner_major, stable=True).indices
+        vf = (order % F).to(torch.int32).contiguous()
+        counts = torch.bincount(corner_major, minlength=num_vertices)
+        off = torch.zeros(num_vertices + 1, dtype=torch.int32, device=faces_i32.device)
+        off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        hit = (off.contiguous(), vf)
+        _csr_cache[key] = hit
+    return hit
+
+
+@dataclass
+class RenderConfig:
+    """Everything of one render call that is not differentiable."""
+    verts: torch.Tensor                 # (V,3) f32 cuda
+    faces: torch.Tensor                 # (F,3) i32 cuda
+    cameras: torch.Tensor               # (B,4,3) f32 cuda
+    proj: tuple                         # (px, py, pz)
+    H: int
+    W: int
+    flags: int
+    interp: str = "nearest"
+    face_uv: torch.Tensor | None = None  # (F,3,2) f32 cuda
+    multiplier: float = 1000.0
+    eps: float = 1e-8
+    lights: torch.Tensor | None = None   # (9) f32 cuda → normals + lighting outputs
+    want_buffers: bool = False           # face_idx / bary / depth extras
+    extras: dict = field(default_factory=dict)
+
+
+def _fill_common(a: LpForwardArgs, cfg: RenderConfig, device):
+    B = cfg.cameras.shape[0]
+    a.verts, a.faces = _ptr(cfg.verts), _ptr(cfg.faces)
+    a.V, a.F = cfg.verts.shape[0], cfg.faces.shape[0]
+    a.cameras, a.B = _ptr(cfg.cameras), B
+    a.proj[0], a.proj[1], a.proj[2] = cfg.proj
+    a.H, a.W = cfg.H, cfg.W
+    a.multiplier, a.eps, a.flags = cfg.multiplier, cfg.eps, cfg.flags
+    nbytes = _lib.lib().lp_workspace_bytes(B, a.F, cfg.H, cfg.W)
+    ws = _workspace(device, nbytes)
+    a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    return ws
+
+
+class _RenderTexture(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, texture, cfg: RenderConfig):
+        _require_cuda(texture, "texture_map")
+        device = texture.device
+        if texture.dim() != 4 or texture.shape[0] != 1:
+            raise ValueError(f"texture_map must have shape (1,C,T,T), got {tuple(texture.shape)}")
+        if cfg.interp not in _INTERP:
+            raise ValueError(f"lp_b200: interpolation mode '{cfg.interp}' is not implemented (nearest, bilinear)")
+        tex = texture.detach().to(torch.float32).contiguous()
+        _, C, Th, Tw = tex.shape
+        B, H, W = cfg.cameras.shape[0], cfg.H, cfg.W
+        image = torch.empty((B, C, H, W), dtype=torch.float32, device=device)
+        mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=device)
+        uv = torch.empty((B, H, W, 2), dtype=torch.float32, device=device)
+        face_idx = bary = depth = normals = lighting = None
+        a = LpForwardArgs()
+        with torch.cuda.device(device):
+            ws = _fill_common(a, cfg, device)
+            a.face_uv, a.texture = _ptr(cfg.face_uv), _ptr(tex)
+            a.C, a.Th, a.Tw, a.interp = C, Th, Tw, _INTERP[cfg.interp]
+            if cfg.want_buffers:
+                face_idx = torch.empty((B, H, W), dtype=torch.int32, device=device)
+                bary = torch.empty((B, H, W, 3), dtype=torch.float32, device=device)
+                depth = torch.empty((B, H, W), dtype=torch.float32, device=device)
+                a.face_idx, a.bary, a.depth = _ptr(face_idx), _ptr(bary), _ptr(depth)
+            keep = [ws, tex]
+            if cfg.lights is not None:
+                off, vf = vertex_face_csr(cfg.faces, a.V)
+                fn = torch.empty((B, a.F, 3), dtype=torch.float32, device=device)
+                vn = torch.empty((B, a.V, 3), dtype=torch.float32, device=device)
+                normals = torch.empty((B, 3, H, W), dtype=torch.float32, device=device)
+                lighting = torch.empty((B, 1, H, W), dtype=torch.float32, device=device)
+                a.vf_offsets, a.vf_faces, a.face_normals, a.vertex_normals = _ptr(off), _ptr(vf), _ptr(fn), _ptr(vn)
+                a.lights, a.normals, a.lighting = _ptr(cfg.lights), _ptr(normals), _ptr(lighting)
+                keep += [off, vf, fn, vn]
+            a.image, a.mask, a.uv = _ptr(image), _ptr(mask), _ptr(uv)
+            _lib.check(_lib.lib().lp_render_forward(ctypes.byref(a), _stream(device)))
+            launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        ctx.cfg = cfg
+        ctx.tex_shape = tuple(texture.shape)
+        ctx.save_for_backward(uv)
+        outs = (image, mask, uv, face_idx, bary, depth, normals, lighting)
+        ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, grad_image, *unused):
+        (uv,) = ctx.saved_tensors
+        cfg = ctx.cfg
+        device = uv.device
+        _, C, Th, Tw = ctx.tex_shape
+        g = grad_image.to(torch.float32).contiguous()
+        grad_tex = torch.zeros((1, C, Th, Tw), dtype=torch.float32, device=device)
+        b = LpBackwardArgs()
+        b.B, b.H, b.W, b.flags = uv.shape[0], cfg.H, cfg.W, cfg.flags
+        b.grad_image, b.uv = _ptr(g), _ptr(uv)
+        b.C, b.Th, b.Tw, b.interp = C, Th, Tw, _INTERP[cfg.interp]
+        b.grad_texture = _ptr(grad_tex)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().lp_render_backward(ctypes.byref(b), _stream(device)))
+            launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        return grad_tex, None
+
+
+class _RenderFeatures(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, face_features, cfg: RenderConfig):
+        _require_cuda(face_features, "face_attributes")
+        device = face_features.device
+        ff = face_features.detach().to(torch.float32).contiguous()
+        if ff.dim() != 4 or ff.shape[2] != 3:
+            raise ValueError(f"face_attributes must have shape (1|B,F,3,D), got {tuple(ff.shape)}")
+        B, H, W = cfg.cameras.shape[0], cfg.H, cfg.W
+        Bf, F, _, D = ff.shape
+        if Bf not in (1, B) or F != cfg.faces.shape[0]:
+            raise ValueError("face_attributes batch/face count does not match the mesh / views")
+        image = torch.empty((B, D, H, W), dtype=torch.float32, device=device)
+        mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=device)
+        face_idx = torch.empty((B, H, W), dtype=torch.int32, device=device)
+        bary = torch.empty((B, H, W, 3), dtype=torch.float32, device=device)
+        depth = torch.empty((B, H, W), dtype=torch.float32, device=device) if cfg.want_buffers else None
+        a = LpForwardArgs()
+        with torch.cuda.device(device):
+            ws = _fill_common(a, cfg, device)
+            a.flags = cfg.flags | _lib.LP_FLAG_SHADE_FEATURES
+            a.face_features, a.D, a.features_batched = _ptr(ff), D, int(Bf == B and B > 1)
+            a.image, a.mask, a.face_idx, a.bary, a.depth = _ptr(image), _ptr(mask), _ptr(face_idx), _ptr(bary), _ptr(depth)
+            _lib.check(_lib.lib().lp_render_forward(ctypes.byref(a), _stream(device)))
+            launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        ctx.cfg, ctx.ff_shape, ctx.batched = cfg, tuple(ff.shape), int(Bf == B and B > 1)
+        ctx.save_for_backward(face_idx, bary)
+        ctx.mark_non_differentiable(*[o for o in (mask, face_idx, bary, depth) if o is not None])
+        return image, mask, face_idx, bary, depth
+
+    @staticmethod
+    def backward(ctx, grad_image, *unused):
+        face_idx, bary = ctx.saved_tensors
+        cfg = ctx.cfg
+        device = face_idx.device
+        Bf, F, _, D = ctx.ff_shape
+        g = grad_image.to(torch.float32).contiguous()
+        grad_ff = torch.zeros(ctx.ff_shape, dtype=torch.float32, device=device)
+        b = LpBackwardArgs()
+        b.B, b.H, b.W = face_idx.shape[0], cfg.H, cfg.W
+        b.flags = cfg.flags | _lib.LP_FLAG_SHADE_FEATURES
+        b.grad_image, b.face_idx, b.bary = _ptr(g), _ptr(face_idx), _ptr(bary)
+        b.F, b.D, b.features_batched = F, D, ctx.batched
+        b.grad_face_features = _ptr(grad_ff)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().lp_render_backward(ctypes.byref(b), _stream(device)))
+            launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        return grad_ff, None
+
+
+def render_texture(texture, cfg: RenderConfig):
+    """→ (image (B,C,H,W), mask (B,1,H,W), uv (B,H,W,2), face_idx|None, bary|None, depth|None,
+    normals|None, lighting|None)."""
+    return _RenderTexture.apply(texture, cfg)
+
+
+def render_face_features(face_features, cfg: RenderConfig):
+    """→ (image (B,D,H,W), mask (B,1,H,W), face_idx (B,H,W) i32, bary (B,H,W,3), depth|None)."""
+    return _RenderFeatures.apply(face_features, cfg)
+
+
+def cameras_from_views(elev, azim, radius, look_at_height: float):
+    """Device-side ``get_camera_from_view`` for angle tensors that already live on the GPU."""
+    device = elev.device
+    _require_cuda(elev, "elev")
+    B = elev.numel()
+    e = elev.detach().to(torch.float32).contiguous().reshape(-1)
+    a = azim.detach().to(device=device, dtype=torch.float32).contiguous().reshape(-1)
+    if torch.is_tensor(radius):
+        r = radius.detach().to(device=device, dtype=torch.float32).contiguous().reshape(-1)
+    else:
+        r = torch.full((1,), float(radius), dtype=torch.float32, device=device)
+    stride = 1 if r.numel() == B and B > 1 else 0
+    if r.numel() not in (1, B):
+        raise ValueError("radius must be a scalar or have one entry per view")
+    out = torch.empty((B, 4, 3), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().lp_cameras_from_views(_ptr(e), _ptr(a), _ptr(r), stride, float(look_at_height), B,
+                                                    _ptr(out), _stream(device)))
+        launch_counter["kernels"] += 1
+    return out

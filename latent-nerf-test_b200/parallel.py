@@ -1,0 +1,65 @@
+"""View-sharded data parallelism for the render path.
+
+The reference is single-process; its unit of work is a camera view.  Views are independent, so
+rank r renders the contiguous block ``shard_views(n, r, world)`` of a batch against a replicated
+mesh / texture, scatter-adds into its own texture gradient, and ONE all-reduce(sum) of that
+gradient per step makes every rank's optimiser step identical to the single-GPU step over the
+whole batch (up to fp32 summation order).  One process per GPU, ``torch.distributed`` (NCCL on
+GPUs over NVLink; gloo in the CPU tests) is the plumbing.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(num_views: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Half-open view range of ``rank``: blocks differ by at most one view, earlier ranks get the
+    larger blocks; empty when there are more ranks than views."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, extra = divmod(num_views, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class GradientBucket:
+    """Flat fp32 buffer the learnable render inputs' gradients live in (texture first, then e.g.
+    the background-sphere colours), so a step needs a single in-place all-reduce and no staging
+    copy: ``param.grad`` tensors are views into the bucket."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("GradientBucket needs at least one parameter")
+        device = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, async_op=False):
+        """Sum the bucket over all ranks (no-op without an initialised process group)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def render_views_sharded(render_fn, view_params: dict, num_views: int, group=None):
+    """Call ``render_fn(**shard)`` on this rank's slice of every per-view tensor in
+    ``view_params`` (tensors whose first dimension is ``num_views``; everything else is passed
+    through).  Returns ``(outputs, (lo, hi))``; ``outputs`` is None for an empty shard."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    lo, hi = shard_views(num_views, rank, world)
+    if hi == lo:
+        return None, (lo, hi)
+    shard = {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == num_views else v)
+             for k, v in view_params.items()}
+    return render_fn(**shard), (lo, hi)

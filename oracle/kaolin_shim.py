@@ -46,6 +46,10 @@ REJECT_BEHIND_CAMERA = True
 DEFAULT_MULTIPLIER = 1000.0
 DEFAULT_EPS = 1e-8
 
+#: buffers of the most recent rasterize() call, for tests that run the reference's glue
+#: (which returns neither face_idx nor the interpolated UVs)
+LAST = {}
+
 _LIB = None
 
 
@@ -249,12 +253,15 @@ def _interpolate(face_idx, w, face_features):
 def rasterize(height, width, face_vertices_z, face_vertices_image, face_features, valid_faces=None,
               multiplier=None, eps=None, backend="cuda"):
     """→ (interpolated_features (B,H,W,D) or a tuple of them, face_idx (B,H,W) int64)."""
-    face_idx, w, _ = rasterize_buffers(height, width, face_vertices_z, face_vertices_image, valid_faces,
-                                       multiplier, eps)
+    face_idx, w, depth = rasterize_buffers(height, width, face_vertices_z, face_vertices_image, valid_faces,
+                                           multiplier, eps)
     if isinstance(face_features, (list, tuple)):
         feats = tuple(_interpolate(face_idx, w, f) for f in face_features)
     else:
         feats = _interpolate(face_idx, w, face_features)
+    LAST.clear()
+    LAST.update(face_idx=face_idx, bary=w, depth=depth,
+                features=feats[0].detach() if isinstance(feats, tuple) else feats.detach())
     return feats, face_idx
 
 

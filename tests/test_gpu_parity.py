@@ -1,0 +1,336 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the
+reference-shaped Renderer classes and through the C ABI, against the frozen reference-glue
+vectors and against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): face_idx and the 0/1 mask bit-exact; pixels, float mask,
+normals, lighting and gradients within rtol 1e-4 / atol 1e-5.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import latent_nerf_test_b200 as lp
+from latent_nerf_test_b200 import _lib, functional
+from oracle import kaolin_shim as kal
+from oracle import renderer_ref
+from tests.common import assert_close, latent_paint_views, load_golden, mesh_views, rnd, scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    kal.RASTER_IMPL = "bbox"
+
+
+class _Mesh:
+    def __init__(self, vertices, faces):
+        self.vertices, self.faces = vertices, faces
+
+
+# ------------------------------------------------------------------ golden vectors (reference glue)
+@pytest.mark.parametrize("case", ["lp_blub_nearest", "lp_blub_bilinear_white"])
+def test_golden_latent_paint_texture(case):
+    gd = load_golden(case)
+    verts, faces, uv = scene(str(gd["shape"]), float(gd["scale"]), float(gd["dy"]))
+    tex = torch.tensor(gd["texture"], device=DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=tuple(int(d) for d in gd["dims"]), interpolation_mode=str(gd["mode"]))
+    r.keep_buffers = True
+    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=float(gd["elev"]),
+                                               azim=float(gd["azim"]), radius=float(gd["radius"]),
+                                               look_at_height=float(gd["dy"]), white_background=bool(gd["white"]))
+    assert image.shape == gd["image"].shape and mask.shape == gd["mask"].shape and image.dtype == torch.float32
+    assert np.array_equal(r.last_buffers["face_idx"].cpu().numpy(), gd["face_idx"])
+    assert np.array_equal(mask.cpu().numpy(), gd["mask"])
+    assert_close(image, gd["image"], "image")
+    covered = torch.tensor(gd["face_idx"]) >= 0
+    assert_close(r.last_buffers["uv"].cpu()[covered], torch.tensor(gd["uv"])[covered], "uv")
+    image.backward(torch.tensor(gd["grad_image"], device=DEV))
+    assert tex.grad.shape == gd["grad_texture"].shape
+    assert_close(tex.grad, gd["grad_texture"], "grad_texture")
+
+
+def test_golden_env_sphere_face_colours():
+    gd = load_golden("lp_env_sphere_colors")
+    m = lp.meshio.find_shape("env_sphere")
+    colors = torch.tensor(gd["colors"], device=DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=tuple(int(d) for d in gd["dims"]))
+    r.keep_buffers = True
+    image, mask = r.render_single_view(_Mesh(m.vertices.to(DEV), m.faces.to(DEV)), colors, elev=float(gd["elev"]),
+                                       azim=float(gd["azim"]), radius=float(gd["radius"]), look_at_height=0.25)
+    assert np.array_equal(r.last_buffers["face_idx"].cpu().numpy(), gd["face_idx"])
+    assert np.array_equal(mask.cpu().numpy(), gd["mask"])
+    assert_close(image, gd["image"], "image")
+    image.backward(torch.tensor(gd["grad_image"], device=DEV))
+    assert_close(colors.grad, gd["grad_colors"], "grad_colors")
+
+
+@pytest.mark.parametrize("case", ["mesh_sphere_body_b3", "mesh_teddy_head_white"])
+def test_golden_mesh_flavour(case):
+    gd = load_golden(case)
+    verts, faces, uv = scene(str(gd["shape"]), 1.0, 0.0)
+    tex = torch.tensor(gd["texture"], device=DEV).requires_grad_(True)
+    dims = tuple(int(d) for d in gd["dims"])
+    r = lp.LatentPaintMeshRenderer(DEV, dim=dims, interpolation_mode="bilinear")
+    r.keep_buffers = True
+    radius = torch.tensor(gd["radius"]) if gd["radius"].ndim else float(gd["radius"])
+    outs = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, torch.tensor(gd["elev"]),
+                                        torch.tensor(gd["azim"]), radius, dims=dims, white_background=bool(gd["white"]),
+                                        is_body=bool(gd["is_body"]))
+    assert np.array_equal(r.last_buffers["face_idx"].cpu().numpy(), gd["face_idx"])
+    for o, k in zip(outs, ("image", "mask", "normals", "lighting")):
+        assert o.shape == gd[k].shape, k
+        assert_close(o, gd[k], k)
+    assert np.array_equal((outs[1] > 0).cpu().numpy(), gd["face_idx"][:, None] >= 0)
+    outs[0].backward(torch.tensor(gd["grad_image"], device=DEV))
+    assert_close(tex.grad, gd["grad_texture"], "grad_texture", rtol=1e-4, atol=2e-5)
+
+
+# ------------------------------------------------------------------ oracle, seeded random views
+def _oracle_latent_paint(verts, faces, uv, tex, mode, dims, e, a, r, dy, white, grad):
+    t = tex.detach().cpu().clone().requires_grad_(True)
+    ref = renderer_ref.LatentPaintRendererRef(dim=dims, interpolation_mode=mode)
+    image, mask = ref.render_single_view_texture(verts, faces, uv, t, elev=e, azim=a, radius=r, look_at_height=dy,
+                                                 dims=dims, white_background=white)
+    image.backward(grad.cpu())
+    return image.detach(), mask, ref.last["face_idx"], t.grad
+
+
+@pytest.mark.parametrize("shape,scale,dy,dims,T,C,mode,white", [
+    ("blub", 0.6, 0.25, (64, 64), 128, 4, "nearest", False),       # config 1
+    ("nascar", 0.6, 0.25, (512, 512), 1024, 3, "bilinear", False),  # config 2 geometry, one view at a time
+    ("teddy", 0.6, 0.25, (200, 120), 64, 4, "bilinear", True),      # non-square, not a multiple of the tile
+    ("sphere", 0.6, 0.25, (33, 47), 20, 5, "nearest", True),        # odd sizes, generic channel count, non-pow2 T
+])
+def test_latent_paint_vs_oracle(shape, scale, dy, dims, T, C, mode, white):
+    verts, faces, uv = scene(shape, scale, dy)
+    radius, theta, phi = latent_paint_views(3, seed=5)
+    tex = rnd((1, C, T, T), 1, 0.4).to(DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=dims, interpolation_mode=mode)
+    r.keep_buffers = True
+    vd, fd, ud = verts.to(DEV), faces.to(DEV), uv.to(DEV)
+    for i in range(3):
+        e, a, rad = float(theta[i]), float(phi[i]), float(radius[i])
+        tex.grad = None
+        image, mask = r.render_single_view_texture(vd, fd, ud, tex, elev=e, azim=a, radius=rad, look_at_height=dy,
+                                                   dims=dims, white_background=white)
+        assert image.shape == (1, C, dims[1], dims[0])
+        g = rnd(tuple(image.shape), 20 + i)
+        image.backward(g.to(DEV))
+        oi, om, ofi, og = _oracle_latent_paint(verts, faces, uv, tex, mode, dims, e, a, rad, dy, white, g)
+        assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ofi), "face_idx must be bit-exact"
+        assert torch.equal(mask.cpu(), om), "mask must be bit-exact"
+        assert_close(image, oi, "image")
+        assert_close(tex.grad, og, "grad_texture")
+        assert int((ofi >= 0).sum()) > 0
+
+
+def test_mesh_flavour_vs_oracle_batched():
+    verts, faces, uv = scene("teddy", 1.0, 0.0)
+    radius, theta, phi = mesh_views(4, seed=9)
+    for is_body, dims, T in [(True, (64, 64), 512), (False, (96, 80), 128)]:
+        tex = rnd((1, 4, T, T), 1, 0.4).to(DEV).requires_grad_(True)
+        r = lp.LatentPaintMeshRenderer(DEV, dim=dims)
+        r.keep_buffers = True
+        outs = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, theta, phi, radius, dims=dims,
+                                            is_body=is_body)
+        g = rnd(tuple(outs[0].shape), 3)
+        outs[0].backward(g.to(DEV))
+        t = tex.detach().cpu().clone().requires_grad_(True)
+        ref = renderer_ref.LatentPaintMeshRendererRef(dim=dims)
+        routs = ref.render_single_view_texture(verts, faces, uv, t, theta, phi, radius, dims=dims, is_body=is_body)
+        routs[0].backward(g)
+        assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ref.last["face_idx"])
+        for o, ro, k in zip(outs, routs, ("image", "mask", "normals", "lighting")):
+            assert_close(o, ro, k)
+        assert_close(tex.grad, t.grad, "grad_texture", rtol=1e-4, atol=1e-4 if is_body else 1e-5)
+
+
+def test_device_cameras_and_visibility_with_them():
+    """Angle tensors on the GPU take lp_cameras_from_views: the matrices match the host math to
+    fp32 rounding, and visibility stays bit-exact when the oracle is fed those same matrices."""
+    verts, faces, uv = scene("sphere", 1.0, 0.0)
+    radius, theta, phi = mesh_views(5, seed=2)
+    r = lp.LatentPaintMeshRenderer(DEV, dim=(64, 64))
+    r.keep_buffers = True
+    cam_dev = r.get_camera_from_view(theta.to(DEV), phi.to(DEV), radius.to(DEV), -0.3)
+    cam_host = renderer_ref._look_at_camera(theta, phi, radius, torch.tensor([-0.3]))
+    assert_close(cam_dev, cam_host, "camera matrices", rtol=1e-5, atol=2e-6)
+    tex = rnd((1, 4, 32, 32), 1).to(DEV)
+    outs = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, theta.to(DEV), phi.to(DEV),
+                                        radius.to(DEV), is_body=True)
+    M = r.last_buffers["camera"].cpu()
+    fvc, fvi, fn = kal.prepare_vertices(verts, faces, kal.generate_perspective_projection(np.pi / 4), camera_transform=M)
+    idx, _, _ = kal.rasterize_buffers(64, 64, fvc[..., -1], fvi, valid_faces=fn[..., -1].abs() > 0)
+    assert torch.equal(r.last_buffers["face_idx"].cpu().long(), idx)
+    assert outs[0].shape == (5, 4, 64, 64)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_view_and_huge_triangles():
+    verts, faces, uv = scene("sphere", 0.6, 0.25)
+    tex = rnd((1, 4, 16, 16), 1).to(DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=(40, 40), interpolation_mode="bilinear")
+    r.keep_buffers = True
+    # look far above the mesh: nothing is visible
+    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2,
+                                               look_at_height=50.0)
+    assert float(mask.sum()) == 0 and float(image.abs().sum()) == 0
+    image.sum().backward()
+    assert float(tex.grad.abs().sum()) == 0
+    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2,
+                                               look_at_height=50.0, white_background=True)
+    assert float((image - 1).abs().sum()) == 0
+    # a few triangles filling the whole frame exercise the coarse pyramid levels
+    big_v = torch.tensor([[-9.0, -9.0, 0.0], [9.0, -9.0, 0.0], [0.0, 9.0, 0.0], [-9.0, 9.0, -0.5], [9.0, 9.0, -0.5],
+                          [0.0, -9.0, -0.5]])
+    big_f = torch.tensor([[0, 1, 2], [3, 5, 4]])
+    big_uv = torch.rand(1, 2, 3, 2, generator=torch.Generator().manual_seed(0))
+    for dims in [(40, 40), (300, 200)]:
+        image, mask = r.render_single_view_texture(big_v.to(DEV), big_f.to(DEV), big_uv.to(DEV), tex, elev=1.4, azim=0.1,
+                                                   radius=2.0, dims=dims)
+        oi, om, ofi, _ = _oracle_latent_paint(big_v, big_f, big_uv, tex, "bilinear", dims, 1.4, 0.1, 2.0, 0.0, False,
+                                              torch.zeros(1, 4, dims[1], dims[0]))
+        assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ofi)
+        assert_close(image, oi, "image")
+        assert float(om.mean()) > 0.3
+
+
+def test_degenerate_and_behind_camera_faces():
+    """env_sphere encloses the camera: thousands of faces behind / straddling the image plane."""
+    m = lp.meshio.find_shape("env_sphere")
+    colors = rnd((1, m.faces.shape[0], 3, 4), 3)
+    for flag in (True, False):
+        r = lp.LatentPaintRenderer(DEV, dim=(48, 48))
+        r.keep_buffers, r.reject_behind_camera = True, flag
+        image, mask = r.render_single_view(_Mesh(m.vertices.to(DEV), m.faces.to(DEV)), colors.to(DEV), elev=0.8, azim=2.0,
+                                           radius=1.4, look_at_height=0.25)
+        kal.REJECT_BEHIND_CAMERA = flag
+        try:
+            ref = renderer_ref.LatentPaintRendererRef(dim=(48, 48))
+            oi, om = ref.render_single_view(m.vertices, m.faces, colors, elev=0.8, azim=2.0, radius=1.4, look_at_height=0.25)
+        finally:
+            kal.REJECT_BEHIND_CAMERA = True
+        assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ref.last["face_idx"]), f"reject_behind={flag}"
+        assert_close(image, oi, "image")
+
+
+def test_high_poly_stress_against_oracle():
+    """config-4 style: subdivided sphere (81 920 faces, sub-pixel triangles) — bins hold hundreds of faces."""
+    verts, faces, uv = scene("sphere", 0.6, 0.25, subdivide=3)
+    tex = rnd((1, 3, 256, 256), 1).to(DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=(256, 256), interpolation_mode="bilinear")
+    r.keep_buffers = True
+    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=1.1, azim=0.3, radius=1.2,
+                                               look_at_height=0.25)
+    g = rnd(tuple(image.shape), 2)
+    image.backward(g.to(DEV))
+    oi, om, ofi, og = _oracle_latent_paint(verts, faces, uv, tex, "bilinear", (256, 256), 1.1, 0.3, 1.2, 0.25, False, g)
+    assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ofi)
+    assert_close(image, oi, "image")
+    assert_close(tex.grad, og, "grad_texture")
+
+
+# ------------------------------------------------------------------ size-independent properties at config-2 size
+def test_config2_properties():
+    verts, faces, uv = scene("nascar", 0.6, 0.25)
+    vd, fd, ud = verts.to(DEV), faces.to(DEV), uv.to(DEV)
+    r = lp.LatentPaintRenderer(DEV, dim=(512, 512), interpolation_mode="bilinear")
+    r.keep_buffers = True
+    radius, theta, phi = latent_paint_views(8, seed=0)
+    const = torch.full((1, 3, 1024, 1024), 0.625, device=DEV)
+    tex = rnd((1, 3, 1024, 1024), 1, 0.4).to(DEV).requires_grad_(True)
+    for i in range(8):
+        e, a, rad = float(theta[i]), float(phi[i]), float(radius[i])
+        image, mask = r.render_single_view_texture(vd, fd, ud, const, elev=e, azim=a, radius=rad, look_at_height=0.25)
+        fi = r.last_buffers["face_idx"].clone()
+        assert_close(image, 0.625 * mask.expand_as(image), "constant texture → constant · mask")
+        assert torch.equal(mask[0, 0] > 0, fi[0] >= 0)
+        depth = r.last_buffers["depth"]
+        assert bool((depth[fi >= 0] < 0).all()) and bool((depth[fi < 0] == 0).all())
+        bary = r.last_buffers["bary"]
+        assert_close(bary.sum(-1)[fi >= 0], torch.ones(int((fi >= 0).sum())), "barycentrics sum to one", atol=1e-5)
+        # determinism: same buffers bit for bit on a second run
+        image2, _ = r.render_single_view_texture(vd, fd, ud, const, elev=e, azim=a, radius=rad, look_at_height=0.25)
+        assert torch.equal(image, image2) and torch.equal(fi, r.last_buffers["face_idx"])
+        # bilinear taps sum to one ⇒ the gradient mass equals the masked upstream mass
+        tex.grad = None
+        img, msk = r.render_single_view_texture(vd, fd, ud, tex, elev=e, azim=a, radius=rad, look_at_height=0.25)
+        g = rnd(tuple(img.shape), 40 + i).to(DEV)
+        img.backward(g)
+        assert_close(tex.grad.sum(dim=(0, 2, 3)), (g * msk).sum(dim=(0, 2, 3)), "gradient mass", rtol=1e-3, atol=1e-2)
+        # linearity of the backward in the upstream gradient
+        g1 = tex.grad.clone()
+        tex.grad = None
+        img, _ = r.render_single_view_texture(vd, fd, ud, tex, elev=e, azim=a, radius=rad, look_at_height=0.25)
+        img.backward(2.0 * g)
+        assert_close(tex.grad, 2.0 * g1, "backward is linear", rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ C ABI directly
+def test_c_abi_error_codes_on_device():
+    L = _lib.lib()
+    verts, faces, uv = scene("sphere", 0.6, 0.25)
+    v = verts.to(DEV).contiguous()
+    f = faces.to(DEV, torch.int32).contiguous()
+    u = uv.to(DEV).reshape(-1, 3, 2).contiguous()
+    cam = lp.camera.camera_from_view(torch.tensor(1.0), torch.tensor(0.5), 1.3, 0.25).to(DEV).contiguous()
+    tex = rnd((1, 4, 16, 16), 1).to(DEV)
+    image = torch.empty(1, 4, 32, 32, device=DEV)
+    mask = torch.empty(1, 1, 32, 32, device=DEV)
+    a = _lib.LpForwardArgs()
+    a.verts, a.faces, a.V, a.F = v.data_ptr(), f.data_ptr(), v.shape[0], f.shape[0]
+    a.cameras, a.B, a.H, a.W = cam.data_ptr(), 1, 32, 32
+    a.proj[0] = a.proj[1] = 1.7320508; a.proj[2] = -1.0
+    a.multiplier, a.eps, a.flags = 1000.0, 1e-8, _lib.LP_FLAG_MASK_IMAGE | _lib.LP_FLAG_REJECT_BEHIND
+    a.face_uv, a.texture, a.C, a.Th, a.Tw, a.interp = u.data_ptr(), tex.data_ptr(), 4, 16, 16, 0
+    a.image, a.mask = image.data_ptr(), mask.data_ptr()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_WORKSPACE
+    need = L.lp_workspace_bytes(1, f.shape[0], 32, 32)
+    ws = torch.empty(need - 1, dtype=torch.uint8, device=DEV)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_WORKSPACE
+    ws = torch.empty(need, dtype=torch.uint8, device=DEV)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.interp = 2
+    assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_UNSUPPORTED
+    a.interp = 0
+    assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_OK
+    assert L.lp_last_launch_count() == 4
+    torch.cuda.synchronize()
+    assert float(mask.sum()) > 0
+    r = lp.LatentPaintRenderer(DEV, dim=(32, 32), interpolation_mode="bicubic")
+    with pytest.raises(ValueError, match="not implemented"):
+        r.render_single_view_texture(v, faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lp.LatentPaintRenderer(DEV, dim=(32, 32)).render_single_view_texture(v, faces.to(DEV), uv.to(DEV), tex.cpu())
+
+
+def test_host_buffer_step_matches_device_path():
+    """lp_render_step_host (what bench.py's e2e times) gives the same image / gradient as the
+    autograd path."""
+    L = _lib.lib()
+    verts, faces, uv = scene("nascar", 0.6, 0.25)
+    B, H, W, C, T = 2, 128, 128, 3, 256
+    radius, theta, phi = latent_paint_views(B, seed=3)
+    cams = torch.cat([lp.camera.camera_from_view(theta[i], phi[i], float(radius[i]), 0.25) for i in range(B)]).contiguous()
+    tex = rnd((1, C, T, T), 1, 0.4).to(DEV).requires_grad_(True)
+    g = rnd((B, C, H, W), 2)
+    r = lp.LatentPaintRenderer(DEV, dim=(W, H), interpolation_mode="bilinear")
+    imgs = []
+    for i in range(B):
+        img, _ = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=float(theta[i]),
+                                              azim=float(phi[i]), radius=float(radius[i]), look_at_height=0.25)
+        img.backward(g[i:i + 1].to(DEV))
+        imgs.append(img.detach())
+    from bench import HostStep
+    hs = HostStep(verts, faces, uv, tex.detach(), B, H, W, "bilinear", np.pi / 3)
+    image_h, mask_h, grad_h = hs.step(cams, g)
+    assert_close(image_h, torch.cat(imgs), "image through host buffers")
+    assert_close(grad_h, tex.grad[0], "grad_texture through host buffers", rtol=1e-4, atol=2e-5)

@@ -1,0 +1,141 @@
+"""CPU tests of the host side: the C-ABI library builds, loads and exports every symbol the
+header declares (no compute calls — there is no GPU here), the ctypes structs match the C
+layout, and the host logic (camera math, mesh IO, UV atlas, CSR, view sharding) is right."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import latent_nerf_test_b200 as lp
+from latent_nerf_test_b200 import _lib, camera, functional, meshio
+from oracle import kaolin_shim as kal
+from oracle import renderer_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lp_b200.h")
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    src = open(HEADER).read()
+    declared = sorted(set(re.findall(r"\b(lp_[a-z_]+)\s*\(", src)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/lp_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.lp_version() == 100
+    assert L.lp_error_string(3).decode() == "workspace too small"
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                    'sizeof(LpForwardArgs),sizeof(LpBackwardArgs),offsetof(LpForwardArgs,workspace_bytes),'
+                    'offsetof(LpForwardArgs,lights),offsetof(LpBackwardArgs,grad_face_features));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(_lib.LpForwardArgs)
+    assert int(out[1]) == ctypes.sizeof(_lib.LpBackwardArgs)
+    assert int(out[2]) == _lib.LpForwardArgs.workspace_bytes.offset
+    assert int(out[3]) == _lib.LpForwardArgs.lights.offset
+    assert int(out[4]) == _lib.LpBackwardArgs.grad_face_features.offset
+
+
+def test_argument_validation_without_a_gpu():
+    """Bad arguments are rejected before any CUDA call is made."""
+    L = _lib.lib()
+    assert L.lp_render_forward(None, None) == _lib.LP_ERR_BAD_ARG
+    a = _lib.LpForwardArgs()
+    assert L.lp_render_forward(ctypes.byref(a), None) == _lib.LP_ERR_BAD_ARG
+    assert b"verts" in L.lp_last_error()
+    assert L.lp_render_backward(None, None) == _lib.LP_ERR_BAD_ARG
+    assert L.lp_workspace_bytes(0, 10, 10, 10) == 0
+    assert L.lp_workspace_bytes(8, 7500, 512, 512) > 8 * 7500 * 36
+    with pytest.raises(ValueError):
+        _lib.check(_lib.LP_ERR_BAD_ARG)
+
+
+def test_renderer_refuses_cpu():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lp.LatentPaintRenderer("cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lp.LatentPaintMeshRenderer("cpu")
+
+
+def test_host_camera_equals_oracle_camera():
+    for e, a, r, h in [(1.0, 0.7, 1.25, 0.25), (0.3, 5.9, 2.0, 0.0), (2.5, 3.1, 1.0, -0.3)]:
+        mine = camera.camera_from_view(torch.tensor(e), torch.tensor(a), r, h)
+        ref = renderer_ref.LatentPaintRendererRef.get_camera_from_view(torch.tensor(e), torch.tensor(a), r, h)
+        assert mine.shape == (1, 4, 3) and torch.equal(mine, ref)
+    th, ph, rad = torch.tensor([1.2, 1.7, 1.0]), torch.tensor([0.3, 5.0, 2.2]), torch.tensor([1.5, 2.2, 1.9])
+    assert torch.equal(camera.camera_from_view(th, ph, rad, torch.tensor([0.4])),
+                       renderer_ref._look_at_camera(th, ph, rad, torch.tensor([0.4])))
+    M = camera.camera_from_view(th, ph, rad, 0.4)
+    R = M[:, :3, :]
+    assert torch.allclose(R.transpose(1, 2) @ R, torch.eye(3).expand(3, 3, 3), atol=1e-6)
+    assert torch.equal(camera.generate_perspective_projection(np.pi / 3), kal.generate_perspective_projection(np.pi / 3))
+
+
+def test_obj_reader_and_packed_meshes(tmp_path):
+    p = tmp_path / "t.obj"
+    p.write_text("# c\nmtllib x.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvt 0 0\nvt 1 0\nvt 0 1\nvn 0 0 1\n"
+                 "f 1/1/1 2/2/1 3/3/1\nf 1//1 3//1 4//1\nf 2 3 4\n")
+    m = meshio.load_obj(str(p))
+    assert m.vertices.shape == (4, 3) and m.faces.tolist() == [[0, 1, 2], [0, 2, 3], [1, 2, 3]]
+    assert m.face_uvs_idx.tolist() == [[0, 1, 2], [-1, -1, -1], [-1, -1, -1]]
+    assert meshio.face_uv_attributes(m).shape == (1, 3, 3, 2)          # falls back to the atlas
+    for name, V, F in [("blub", 7106, 14208), ("nascar", 3750, 7500), ("teddy", 2892, 5760), ("sphere", 642, 1280),
+                       ("env_sphere", 2562, 5120)]:
+        mm = meshio.load_npz(os.path.join(ROOT, "tests", "golden", "meshes", name + ".npz"))
+        assert mm.vertices.shape == (V, 3) and mm.faces.shape == (F, 3)
+    v = meshio.normalize_vertices(meshio.find_shape("blub").vertices, 0.6, 0.25)
+    c = v - torch.tensor([0.0, 0.25, 0.0])
+    assert abs(float(c.norm(dim=1).max()) - 0.6) < 1e-6 and float(c.mean(0).abs().max()) < 1e-6
+
+
+def test_grid_atlas_and_subdivision():
+    vt, ft = meshio.grid_atlas_uvs(7500)
+    assert vt.shape == (22500, 2) and ft.shape == (7500, 3)
+    assert float(vt.min()) > 0 and float(vt.max()) < 1
+    tri = vt[ft]                                         # (F,3,2); all triangles have the same positive area
+    area = 0.5 * ((tri[:, 1, 0] - tri[:, 0, 0]) * (tri[:, 2, 1] - tri[:, 0, 1]) -
+                  (tri[:, 2, 0] - tri[:, 0, 0]) * (tri[:, 1, 1] - tri[:, 0, 1]))
+    assert torch.allclose(area, area[0].expand_as(area), rtol=1e-3) and float(area[0]) > 0
+    s = meshio.subdivide(meshio.find_shape("sphere"), 2)
+    assert s.faces.shape == (1280 * 16, 3) and s.vertices.shape == (642 + 1920 + 7680, 3)
+    assert torch.allclose(s.vertices.norm(dim=1), torch.ones(s.vertices.shape[0]), atol=1e-5)
+    assert meshio.face_uv_attributes(s).shape == (1, 1280 * 16, 3, 2)
+
+
+def test_vertex_face_csr_order_matches_reference_accumulation():
+    faces = meshio.find_shape("sphere").faces.to(torch.int32)
+    V = int(faces.max()) + 1
+    off, vf = functional.vertex_face_csr(faces, V)
+    assert off[0] == 0 and int(off[-1]) == faces.numel()
+    fn = torch.randn(2, faces.shape[0], 3, generator=torch.Generator().manual_seed(0))
+    ref = renderer_ref.LatentPaintMeshRendererRef.compute_vertex_normals(faces.long(), fn)
+    out = torch.zeros(2, V, 3)
+    for v in range(V):                                   # the exact loop k_vertex_normals runs
+        acc = torch.zeros(2, 3)
+        for i in range(int(off[v]), int(off[v + 1])):
+            acc = acc + fn[:, int(vf[i])]
+        out[:, v] = acc / max(int(off[v + 1]) - int(off[v]), 1)
+    assert torch.equal(out, ref)
+
+
+def test_shard_views():
+    from latent_nerf_test_b200.parallel import shard_views
+    for n, w in [(64, 8), (8, 8), (5, 4), (3, 8), (0, 2)]:
+        spans = [shard_views(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_views(4, 4, 4)
