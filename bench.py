@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--cpu-views", type=int, default=40, help="views timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -360,22 +361,24 @@ def main():
                              "frac": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9 / peak}}
 
         # ---- e2e: host buffers through lp_render_step_host
-        hs = HostStep(verts, faces, uv, sets[0].tex.cpu(), B, H, W, w["interp"], FOV, device=str(device))
-        radius, theta, phi = make_views(B, 77)
-        hs.h_cams.copy_(cameras_for(radius, theta, phi, w["dy"]))
-        hs.h_grad.copy_(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5)))
-        n_e2e = max(5, min(args.steps, 50))
-        with torch.cuda.stream(stream):
-            for _ in range(3):
-                hs.step()
-            torch.cuda.synchronize(device)
-            t0 = time.perf_counter()
-            for _ in range(n_e2e):
-                hs.step()
-            torch.cuda.synchronize(device)
-            e2e_s = time.perf_counter() - t0
-        e2e = {"value": B * n_e2e / e2e_s, "unit": "views/s", "h2d_bytes_per_step": hs.h2d_bytes,
-               "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": 1e3 * e2e_s / n_e2e, "n_gpus": 1}
+        e2e = None
+        if not args.no_e2e:
+            hs = HostStep(verts, faces, uv, sets[0].tex.cpu(), B, H, W, w["interp"], FOV, device=str(device))
+            radius, theta, phi = make_views(B, 77)
+            hs.h_cams.copy_(cameras_for(radius, theta, phi, w["dy"]))
+            hs.h_grad.copy_(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5)))
+            n_e2e = max(5, min(args.steps, 50))
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    hs.step()
+                torch.cuda.synchronize(device)
+                t0 = time.perf_counter()
+                for _ in range(n_e2e):
+                    hs.step()
+                torch.cuda.synchronize(device)
+                e2e_s = time.perf_counter() - t0
+            e2e = {"value": B * n_e2e / e2e_s, "unit": "views/s", "h2d_bytes_per_step": hs.h2d_bytes,
+                   "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": 1e3 * e2e_s / n_e2e, "n_gpus": 1}
 
         # ---- cpu baseline: bounded sample of the same workload on the host cores
         cpu = None

@@ -177,19 +177,25 @@ def test_empty_view_and_huge_triangles():
     tex = rnd((1, 4, 16, 16), 1).to(DEV).requires_grad_(True)
     r = lp.LatentPaintRenderer(DEV, dim=(40, 40), interpolation_mode="bilinear")
     r.keep_buffers = True
-    # look far above the mesh: nothing is visible
-    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2,
-                                               look_at_height=50.0)
+    # the mesh is far outside the frustum: nothing is visible (checked with the oracle: 0 covered pixels)
+    far = (verts + torch.tensor([0.0, -100.0, 0.0])).to(DEV)
+    image, mask = r.render_single_view_texture(far, faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2)
     assert float(mask.sum()) == 0 and float(image.abs().sum()) == 0
     image.sum().backward()
     assert float(tex.grad.abs().sum()) == 0
-    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2,
-                                               look_at_height=50.0, white_background=True)
+    image, mask = r.render_single_view_texture(far, faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2,
+                                               white_background=True)
     assert float((image - 1).abs().sum()) == 0
+    # no near-plane clipping (kaolin semantics): faces straddling the camera plane smear over the frame
+    image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.2,
+                                               look_at_height=50.0)
+    oi, om, ofi, _ = _oracle_latent_paint(verts, faces, uv, tex, "bilinear", (40, 40), 1.0, 0.5, 1.2, 50.0, False,
+                                          torch.zeros(1, 4, 40, 40))
+    assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ofi) and float(om.sum()) == 1600
     # a few triangles filling the whole frame exercise the coarse pyramid levels
-    big_v = torch.tensor([[-9.0, -9.0, 0.0], [9.0, -9.0, 0.0], [0.0, 9.0, 0.0], [-9.0, 9.0, -0.5], [9.0, 9.0, -0.5],
-                          [0.0, -9.0, -0.5]])
-    big_f = torch.tensor([[0, 1, 2], [3, 5, 4]])
+    big_v = torch.tensor([[-9.0, -9.0, 0.0], [9.0, -9.0, 0.0], [0.0, 9.0, 0.0], [-9.0, -9.0, 0.3], [9.0, -9.0, 0.3],
+                          [-9.0, 9.0, 0.3]])
+    big_f = torch.tensor([[0, 1, 2], [3, 4, 5]])
     big_uv = torch.rand(1, 2, 3, 2, generator=torch.Generator().manual_seed(0))
     for dims in [(40, 40), (300, 200)]:
         image, mask = r.render_single_view_texture(big_v.to(DEV), big_f.to(DEV), big_uv.to(DEV), tex, elev=1.4, azim=0.1,
@@ -198,7 +204,7 @@ def test_empty_view_and_huge_triangles():
                                               torch.zeros(1, 4, dims[1], dims[0]))
         assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ofi)
         assert_close(image, oi, "image")
-        assert float(om.mean()) > 0.3
+        assert float(om.mean()) > 0.3 and set(ofi.unique().tolist()) >= {0, 1}
 
 
 def test_degenerate_and_behind_camera_faces():
@@ -302,7 +308,7 @@ def test_c_abi_error_codes_on_device():
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_UNSUPPORTED
     a.interp = 0
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_OK
-    assert L.lp_last_launch_count() == 4
+    assert L.lp_last_launch_count() == 3
     torch.cuda.synchronize()
     assert float(mask.sum()) > 0
     r = lp.LatentPaintRenderer(DEV, dim=(32, 32), interpolation_mode="bicubic")
