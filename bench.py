@@ -82,6 +82,7 @@ class DeviceStep:
         self.mask = torch.empty(B, 1, H, W, device=device)
         self.uv = torch.empty(B, H, W, 2, device=device)
         self.grad_tex = torch.zeros(C, T, T, device=device)
+        self.tile_any = torch.empty(B, (H + 15) // 16, (W + 15) // 16, dtype=torch.uint8, device=device)
         L = _lib.lib()
         self.ws = torch.empty(int(L.lp_workspace_bytes(B, faces.shape[0], H, W)), dtype=torch.uint8, device=device)
         a = _lib.LpForwardArgs()
@@ -96,11 +97,21 @@ class DeviceStep:
         a.interp = _lib.LP_INTERP_BILINEAR if w["interp"] == "bilinear" else _lib.LP_INTERP_NEAREST
         a.image, a.mask, a.uv = self.image.data_ptr(), self.mask.data_ptr(), self.uv.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        a.tile_any = self.tile_any.data_ptr()
         b = _lib.LpBackwardArgs()
         b.B, b.H, b.W, b.flags = B, H, W, a.flags
         b.grad_image, b.uv = self.grad_image.data_ptr(), self.uv.data_ptr()
         b.C, b.Th, b.Tw, b.interp = C, T, T, a.interp
         b.grad_texture = self.grad_tex.data_ptr()
+        b.tile_any = self.tile_any.data_ptr()
+        self.accum = torch.empty(int(L.lp_backward_workspace_bytes(C, T, T)), dtype=torch.uint8, device=device)
+        if self.accum.numel() and os.environ.get("LP_BWD_VEC", "0") == "1":
+            b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
+            b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
+        else:
+            self.accum = self.accum[:0]
+        if os.environ.get("LP_DEBUG_NO_ATOMICS") == "1":
+            b.flags |= 1 << 30
         self.fwd, self.bwd = a, b
         self.keep = (verts, faces, uv)
         self.launches = 0
@@ -111,7 +122,8 @@ class DeviceStep:
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(L.lp_render_forward(ctypes.byref(self.fwd), stream))
         n = L.lp_last_launch_count()
-        self.grad_tex.zero_()
+        if not self.accum.numel():
+            self.grad_tex.zero_()
         _lib.check(L.lp_render_backward(ctypes.byref(self.bwd), stream))
         self.launches = n + L.lp_last_launch_count()
 

@@ -60,8 +60,10 @@ enum {
     LP_FLAG_REJECT_BEHIND    = 1u << 2, /* faces whose interpolated depth is not < 0 never win (BASELINE.md decree 3) */
     LP_FLAG_CULL_NZ_ZERO     = 1u << 3, /* drop faces whose unit camera-space normal has |n_z| == 0:
                                            dibr_rasterization's valid_faces as the reference calls it with abs() */
-    LP_FLAG_SHADE_FEATURES   = 1u << 4  /* interpolate face_features instead of sampling a texture
+    LP_FLAG_SHADE_FEATURES   = 1u << 4, /* interpolate face_features instead of sampling a texture
                                            (Renderer.render_single_view, latent_paint render.py:34-47) */
+    LP_FLAG_GRAD_OVERWRITE   = 1u << 5  /* lp_render_backward with a workspace: grad_texture is written, not
+                                           accumulated into, so the caller need not zero it */
 };
 
 typedef struct LpForwardArgs {
@@ -102,6 +104,8 @@ typedef struct LpForwardArgs {
     float         *depth;          /* (B,H,W) camera-space z of the visible surface, 0 = none */
     float         *normals;        /* (B,3,H,W) interpolated averaged vertex normals */
     float         *lighting;       /* (B,1,H,W) clamp(SH(normals)·lights, 1e-8, 1) */
+    uint8_t       *tile_any;       /* optional (B, ceil(H/16), ceil(W/16)): 1 where the 16x16 tile holds a covered
+                                      pixel; pass the same buffer to lp_render_backward to skip empty tiles */
     /* scratch */
     void          *workspace;
     uint64_t       workspace_bytes;
@@ -120,6 +124,12 @@ typedef struct LpBackwardArgs {
     const float   *bary;           /* (B,H,W,3) */
     int32_t        F, D, features_batched;
     float         *grad_face_features; /* (Bf,F,3,D); ACCUMULATED into */
+    const uint8_t *tile_any;       /* optional, written by the forward call (used with LP_FLAG_MASK_IMAGE) */
+    /* optional scratch of lp_backward_workspace_bytes(): with it (and C <= 4) the taps are accumulated with
+       16-byte vector REDs into a texel-interleaved (Th,Tw,4) buffer and then unpacked into grad_texture —
+       a third of the atomic operations of the planar path */
+    void          *workspace;
+    uint64_t       workspace_bytes;
 } LpBackwardArgs;
 
 int         lp_version(void);
@@ -132,6 +142,8 @@ uint64_t    lp_workspace_bytes(int32_t B, int32_t F, int32_t H, int32_t W);
 /* elev/azim/radius: (B) device arrays (radius_stride 0 broadcasts one value); cameras out (B,4,3) */
 int lp_cameras_from_views(const float *elev, const float *azim, const float *radius, int32_t radius_stride,
                           float look_at_height, int32_t B, float *cameras, void *stream);
+
+uint64_t    lp_backward_workspace_bytes(int32_t C, int32_t Th, int32_t Tw);
 
 int lp_render_forward(const LpForwardArgs *args, void *stream);
 int lp_render_backward(const LpBackwardArgs *args, void *stream);

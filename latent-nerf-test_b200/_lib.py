@@ -28,10 +28,11 @@ LP_FLAG_WHITE_BACKGROUND = 1 << 1
 LP_FLAG_REJECT_BEHIND = 1 << 2
 LP_FLAG_CULL_NZ_ZERO = 1 << 3
 LP_FLAG_SHADE_FEATURES = 1 << 4
+LP_FLAG_GRAD_OVERWRITE = 1 << 5
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes"]
 
 
 class LpForwardArgs(Structure):
@@ -45,7 +46,7 @@ class LpForwardArgs(Structure):
         ("vf_offsets", c_void_p), ("vf_faces", c_void_p), ("face_normals", c_void_p), ("vertex_normals", c_void_p),
         ("lights", c_void_p),
         ("image", c_void_p), ("mask", c_void_p), ("uv", c_void_p), ("face_idx", c_void_p), ("bary", c_void_p),
-        ("depth", c_void_p), ("normals", c_void_p), ("lighting", c_void_p),
+        ("depth", c_void_p), ("normals", c_void_p), ("lighting", c_void_p), ("tile_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
     ]
 
@@ -58,7 +59,8 @@ class LpBackwardArgs(Structure):
         ("grad_texture", c_void_p),
         ("face_idx", c_void_p), ("bary", c_void_p),
         ("F", c_int32), ("D", c_int32), ("features_batched", c_int32),
-        ("grad_face_features", c_void_p),
+        ("grad_face_features", c_void_p), ("tile_any", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_uint64),
     ]
 
 
@@ -99,6 +101,8 @@ def lib() -> ctypes.CDLL:
     L.lp_error_string.argtypes = [c_int32]
     L.lp_workspace_bytes.restype = c_uint64
     L.lp_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    L.lp_backward_workspace_bytes.restype = c_uint64
+    L.lp_backward_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
     L.lp_cameras_from_views.restype = c_int32
     L.lp_cameras_from_views.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_void_p, c_void_p]
     L.lp_render_forward.restype = c_int32

@@ -161,28 +161,38 @@ class _RenderTexture(torch.autograd.Function):
                 a.lights, a.normals, a.lighting = _ptr(cfg.lights), _ptr(normals), _ptr(lighting)
                 keep += [off, vf, fn, vn]
             a.image, a.mask, a.uv = _ptr(image), _ptr(mask), _ptr(uv)
+            tile_any = torch.empty((B, (H + 15) // 16, (W + 15) // 16), dtype=torch.uint8, device=device)
+            a.tile_any = _ptr(tile_any)
             _lib.check(_lib.lib().lp_render_forward(ctypes.byref(a), _stream(device)))
             launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
         ctx.cfg = cfg
         ctx.tex_shape = tuple(texture.shape)
-        ctx.save_for_backward(uv)
+        ctx.save_for_backward(uv, tile_any)
         outs = (image, mask, uv, face_idx, bary, depth, normals, lighting)
         ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
         return outs
 
     @staticmethod
     def backward(ctx, grad_image, *unused):
-        (uv,) = ctx.saved_tensors
+        uv, tile_any = ctx.saved_tensors
         cfg = ctx.cfg
         device = uv.device
         _, C, Th, Tw = ctx.tex_shape
         g = grad_image.to(torch.float32).contiguous()
-        grad_tex = torch.zeros((1, C, Th, Tw), dtype=torch.float32, device=device)
         b = LpBackwardArgs()
         b.B, b.H, b.W, b.flags = uv.shape[0], cfg.H, cfg.W, cfg.flags
+        wbytes = _lib.lib().lp_backward_workspace_bytes(C, Th, Tw)
+        if wbytes:       # vector-RED path: the library zeroes its accumulation buffer and overwrites the gradient
+            accum = torch.empty(int(wbytes), dtype=torch.uint8, device=device)
+            b.workspace, b.workspace_bytes = _ptr(accum), accum.numel()
+            b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
+            grad_tex = torch.empty((1, C, Th, Tw), dtype=torch.float32, device=device)
+        else:
+            grad_tex = torch.zeros((1, C, Th, Tw), dtype=torch.float32, device=device)
         b.grad_image, b.uv = _ptr(g), _ptr(uv)
         b.C, b.Th, b.Tw, b.interp = C, Th, Tw, _INTERP[cfg.interp]
         b.grad_texture = _ptr(grad_tex)
+        b.tile_any = _ptr(tile_any)
         with torch.cuda.device(device):
             _lib.check(_lib.lib().lp_render_backward(ctypes.byref(b), _stream(device)))
             launch_counter["kernels"] += _lib.lib().lp_last_launch_count()

@@ -36,7 +36,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "lp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
                     'sizeof(LpForwardArgs),sizeof(LpBackwardArgs),offsetof(LpForwardArgs,workspace_bytes),'
-                    'offsetof(LpForwardArgs,lights),offsetof(LpBackwardArgs,grad_face_features));return 0;}\n')
+                    'offsetof(LpForwardArgs,lights),offsetof(LpBackwardArgs,workspace_bytes));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
@@ -44,7 +44,7 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     assert int(out[1]) == ctypes.sizeof(_lib.LpBackwardArgs)
     assert int(out[2]) == _lib.LpForwardArgs.workspace_bytes.offset
     assert int(out[3]) == _lib.LpForwardArgs.lights.offset
-    assert int(out[4]) == _lib.LpBackwardArgs.grad_face_features.offset
+    assert int(out[4]) == _lib.LpBackwardArgs.workspace_bytes.offset
 
 
 def test_argument_validation_without_a_gpu():
