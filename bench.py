@@ -296,13 +296,17 @@ def main():
                 graphs = None
     launches_per_step = sets[0].launches
 
-    def one_step(i):
+    def local_step(i):
         k = i % len(sets)
         if graphs is not None:
             graphs[k].replay()
         else:
             sets[k].run()
-        if world > 1:
+        return k
+
+    def one_step(i):
+        k = local_step(i)
+        if world > 1:                      # the path's one exchange: sum the texture gradient over the ranks
             dist.all_reduce(sets[k].grad_tex)
 
     def barrier():
@@ -329,7 +333,7 @@ def main():
             t_end = time.time() + 0.5
             while time.time() < t_end:
                 for i in range(50):
-                    one_step(i)
+                    local_step(i)              # no collective here: the other ranks are not in this loop
                 torch.cuda.synchronize(device)
         clocks = sampler.summary() if sampler else None
     if world > 1:
