@@ -112,6 +112,8 @@ class DeviceStep:
             self.accum = self.accum[:0]
         if os.environ.get("LP_DEBUG_NO_ATOMICS") == "1":
             b.flags |= 1 << 30
+        if os.environ.get("LP_DEBUG_BWD_STOP"):
+            b.flags |= 1 << int(os.environ["LP_DEBUG_BWD_STOP"])
         self.fwd, self.bwd = a, b
         self.keep = (verts, faces, uv)
         self.launches = 0
