@@ -98,8 +98,10 @@ class DeviceStep:
         a.image, a.mask, a.uv = self.image.data_ptr(), self.mask.data_ptr(), self.uv.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
         a.tile_any = self.tile_any.data_ptr()
+        if os.environ.get("LP_DEBUG_FWD_STOP"):
+            a.flags |= 1 << int(os.environ["LP_DEBUG_FWD_STOP"])
         b = _lib.LpBackwardArgs()
-        b.B, b.H, b.W, b.flags = B, H, W, a.flags
+        b.B, b.H, b.W, b.flags = B, H, W, a.flags & 0xff
         b.grad_image, b.uv = self.grad_image.data_ptr(), self.uv.data_ptr()
         b.C, b.Th, b.Tw, b.interp = C, T, T, a.interp
         b.grad_texture = self.grad_tex.data_ptr()

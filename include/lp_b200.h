@@ -105,7 +105,8 @@ typedef struct LpForwardArgs {
     float         *normals;        /* (B,3,H,W) interpolated averaged vertex normals */
     float         *lighting;       /* (B,1,H,W) clamp(SH(normals)·lights, 1e-8, 1) */
     uint8_t       *tile_any;       /* optional (B, ceil(H/16), ceil(W/16)): 1 where the 16x16 tile holds a covered
-                                      pixel; pass the same buffer to lp_render_backward to skip empty tiles */
+                                      pixel.  With LP_FLAG_MASK_IMAGE the saved uv of the other tiles is then NOT
+                                      written, so the same buffer must be passed to lp_render_backward */
     /* scratch */
     void          *workspace;
     uint64_t       workspace_bytes;
