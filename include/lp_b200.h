@@ -71,6 +71,11 @@ typedef struct LpForwardArgs {
     const float   *verts;          /* (V,3) */
     const int32_t *faces;          /* (F,3) */
     int32_t        V, F;
+    /* alternative geometry input = kal.render.mesh.rasterize's own arguments (verts/faces/cameras unused):
+       vertices already projected by the caller */
+    const float   *face_vertices_image; /* (B,F,3,2) NDC xy, or NULL for the vertex path */
+    const float   *face_vertices_z;     /* (B,F,3) camera-space z */
+    const uint8_t *valid_faces;         /* (B,F) or NULL: 0 drops the face (dibr_rasterization's back-face rule) */
     /* views */
     const float   *cameras;        /* (B,4,3) look-at matrices [R;t]: v_cam = [v,1] @ M */
     int32_t        B;
@@ -120,6 +125,8 @@ typedef struct LpBackwardArgs {
     const float   *uv;             /* (B,H,W,2) saved by the forward */
     int32_t        C, Th, Tw, interp;
     float         *grad_texture;   /* (C,Th,Tw) planar; ACCUMULATED into (caller zeroes it) */
+    int64_t        grad_texture_batch_stride; /* elements between the textures of consecutive views; 0 = one
+                                      texture shared by all views (the kaolin-level texture_mapping takes (B,C,T,T)) */
     /* face-feature path */
     const int32_t *face_idx;       /* (B,H,W) */
     const float   *bary;           /* (B,H,W,3) */
@@ -132,6 +139,17 @@ typedef struct LpBackwardArgs {
     void          *workspace;
     uint64_t       workspace_bytes;
 } LpBackwardArgs;
+
+/* kal.render.mesh.texture_mapping forward (latent_paint render.py:64, latent_paint_mesh render.py:243):
+ * clamp, flip v, ATen grid_sample(align_corners=False, padding_mode='border') texel arithmetic */
+typedef struct LpTextureMapArgs {
+    int32_t        B, H, W;
+    const float   *uv;             /* (B,H,W,2) texture coordinates */
+    const float   *texture;        /* (Bt,C,Th,Tw) planar, Bt = 1 (stride 0) or B */
+    int64_t        texture_batch_stride;
+    int32_t        C, Th, Tw, interp;
+    float         *out;            /* (B,C,H,W) */
+} LpTextureMapArgs;
 
 int         lp_version(void);
 const char *lp_last_error(void);
@@ -148,6 +166,7 @@ uint64_t    lp_backward_workspace_bytes(int32_t C, int32_t Th, int32_t Tw);
 
 int lp_render_forward(const LpForwardArgs *args, void *stream);
 int lp_render_backward(const LpBackwardArgs *args, void *stream);
+int lp_texture_map_forward(const LpTextureMapArgs *args, void *stream);
 
 /* vertex → incident (corner-major, face-ascending) CSR: offsets (V+1), entries (3F) hold face ids.
  * face_normals (B,F,3) → vertex_normals (B,V,3) = mean of incident unit face normals, not re-normalised */

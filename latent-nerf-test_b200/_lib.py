@@ -32,12 +32,13 @@ LP_FLAG_GRAD_OVERWRITE = 1 << 5
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward"]
 
 
 class LpForwardArgs(Structure):
     _fields_ = [
         ("verts", c_void_p), ("faces", c_void_p), ("V", c_int32), ("F", c_int32),
+        ("face_vertices_image", c_void_p), ("face_vertices_z", c_void_p), ("valid_faces", c_void_p),
         ("cameras", c_void_p), ("B", c_int32), ("proj", c_float * 3), ("H", c_int32), ("W", c_int32),
         ("multiplier", c_float), ("eps", c_float), ("flags", c_uint32),
         ("face_uv", c_void_p), ("texture", c_void_p), ("C", c_int32), ("Th", c_int32), ("Tw", c_int32),
@@ -56,11 +57,19 @@ class LpBackwardArgs(Structure):
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("flags", c_uint32),
         ("grad_image", c_void_p), ("uv", c_void_p),
         ("C", c_int32), ("Th", c_int32), ("Tw", c_int32), ("interp", c_int32),
-        ("grad_texture", c_void_p),
+        ("grad_texture", c_void_p), ("grad_texture_batch_stride", ctypes.c_int64),
         ("face_idx", c_void_p), ("bary", c_void_p),
         ("F", c_int32), ("D", c_int32), ("features_batched", c_int32),
         ("grad_face_features", c_void_p), ("tile_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
+    ]
+
+
+class LpTextureMapArgs(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("uv", c_void_p), ("texture", c_void_p),
+        ("texture_batch_stride", ctypes.c_int64), ("C", c_int32), ("Th", c_int32), ("Tw", c_int32), ("interp", c_int32),
+        ("out", c_void_p),
     ]
 
 
@@ -109,6 +118,8 @@ def lib() -> ctypes.CDLL:
     L.lp_render_forward.argtypes = [POINTER(LpForwardArgs), c_void_p]
     L.lp_render_backward.restype = c_int32
     L.lp_render_backward.argtypes = [POINTER(LpBackwardArgs), c_void_p]
+    L.lp_texture_map_forward.restype = c_int32
+    L.lp_texture_map_forward.argtypes = [POINTER(LpTextureMapArgs), c_void_p]
     L.lp_vertex_normals.restype = c_int32
     L.lp_vertex_normals.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     L.lp_render_step_host.restype = c_int32

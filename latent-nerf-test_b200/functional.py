@@ -94,9 +94,9 @@ def vertex_face_csr(faces_i32, num_vertices):
 @dataclass
 class RenderConfig:
     """Everything of one render call that is not differentiable."""
-    verts: torch.Tensor                 # (V,3) f32 cuda
-    faces: torch.Tensor                 # (F,3) i32 cuda
-    cameras: torch.Tensor               # (B,4,3) f32 cuda
+    verts: torch.Tensor | None          # (V,3) f32 cuda        (None with the prepared-geometry input)
+    faces: torch.Tensor | None          # (F,3) i32 cuda
+    cameras: torch.Tensor | None        # (B,4,3) f32 cuda
     proj: tuple                         # (px, py, pz)
     H: int
     W: int
@@ -108,13 +108,30 @@ class RenderConfig:
     lights: torch.Tensor | None = None   # (9) f32 cuda → normals + lighting outputs
     want_buffers: bool = False           # face_idx / bary / depth extras
     extras: dict = field(default_factory=dict)
+    # kaolin-level geometry input (kal.render.mesh.rasterize): already projected vertices
+    fvi: torch.Tensor | None = None      # (B,F,3,2) f32 cuda
+    fvz: torch.Tensor | None = None      # (B,F,3) f32 cuda
+    valid: torch.Tensor | None = None    # (B,F) u8 cuda
+
+    @property
+    def B(self):
+        return self.fvz.shape[0] if self.fvi is not None else self.cameras.shape[0]
+
+    @property
+    def F(self):
+        return self.fvz.shape[1] if self.fvi is not None else self.faces.shape[0]
 
 
 def _fill_common(a: LpForwardArgs, cfg: RenderConfig, device):
-    B = cfg.cameras.shape[0]
-    a.verts, a.faces = _ptr(cfg.verts), _ptr(cfg.faces)
-    a.V, a.F = cfg.verts.shape[0], cfg.faces.shape[0]
-    a.cameras, a.B = _ptr(cfg.cameras), B
+    B = cfg.B
+    if cfg.fvi is not None:
+        a.face_vertices_image, a.face_vertices_z, a.valid_faces = _ptr(cfg.fvi), _ptr(cfg.fvz), _ptr(cfg.valid)
+        a.V, a.F = 0, cfg.F
+    else:
+        a.verts, a.faces = _ptr(cfg.verts), _ptr(cfg.faces)
+        a.V, a.F = cfg.verts.shape[0], cfg.faces.shape[0]
+        a.cameras = _ptr(cfg.cameras)
+    a.B = B
     a.proj[0], a.proj[1], a.proj[2] = cfg.proj
     a.H, a.W = cfg.H, cfg.W
     a.multiplier, a.eps, a.flags = cfg.multiplier, cfg.eps, cfg.flags
@@ -135,7 +152,7 @@ class _RenderTexture(torch.autograd.Function):
             raise ValueError(f"lp_b200: interpolation mode '{cfg.interp}' is not implemented (nearest, bilinear)")
         tex = texture.detach().to(torch.float32).contiguous()
         _, C, Th, Tw = tex.shape
-        B, H, W = cfg.cameras.shape[0], cfg.H, cfg.W
+        B, H, W = cfg.B, cfg.H, cfg.W
         image = torch.empty((B, C, H, W), dtype=torch.float32, device=device)
         mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=device)
         uv = torch.empty((B, H, W, 2), dtype=torch.float32, device=device)
@@ -207,9 +224,9 @@ class _RenderFeatures(torch.autograd.Function):
         ff = face_features.detach().to(torch.float32).contiguous()
         if ff.dim() != 4 or ff.shape[2] != 3:
             raise ValueError(f"face_attributes must have shape (1|B,F,3,D), got {tuple(ff.shape)}")
-        B, H, W = cfg.cameras.shape[0], cfg.H, cfg.W
+        B, H, W = cfg.B, cfg.H, cfg.W
         Bf, F, _, D = ff.shape
-        if Bf not in (1, B) or F != cfg.faces.shape[0]:
+        if Bf not in (1, B) or F != cfg.F:
             raise ValueError("face_attributes batch/face count does not match the mesh / views")
         image = torch.empty((B, D, H, W), dtype=torch.float32, device=device)
         mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=device)
@@ -280,3 +297,53 @@ def cameras_from_views(elev, azim, radius, look_at_height: float):
                                                     _ptr(out), _stream(device)))
         launch_counter["kernels"] += 1
     return out
+
+
+class _TextureMap(torch.autograd.Function):
+    """``kal.render.mesh.texture_mapping``: uv (B,H,W,2), textures (B|1,C,T,T) → (B,C,H,W)."""
+
+    @staticmethod
+    def forward(ctx, texture_maps, uv, mode):
+        _require_cuda(texture_maps, "texture_maps")
+        if mode not in _INTERP:
+            raise ValueError(f"lp_b200: interpolation mode '{mode}' is not implemented (nearest, bilinear)")
+        device = texture_maps.device
+        tex = texture_maps.detach().to(torch.float32).contiguous()
+        uvc = uv.detach().to(device=device, dtype=torch.float32).contiguous()
+        B, H, W = uvc.shape[0], uvc.shape[1], uvc.shape[2]
+        Bt, C, Th, Tw = tex.shape
+        if Bt not in (1, B):
+            raise ValueError("texture_maps batch must be 1 or match the coordinates")
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=device)
+        a = _lib.LpTextureMapArgs()
+        a.B, a.H, a.W, a.uv, a.texture = B, H, W, _ptr(uvc), _ptr(tex)
+        a.texture_batch_stride = C * Th * Tw if Bt == B and B > 1 else 0
+        a.C, a.Th, a.Tw, a.interp, a.out = C, Th, Tw, _INTERP[mode], _ptr(out)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().lp_texture_map_forward(ctypes.byref(a), _stream(device)))
+            launch_counter["kernels"] += 1
+        ctx.mode, ctx.tex_shape = mode, tuple(tex.shape)
+        ctx.save_for_backward(uvc)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (uvc,) = ctx.saved_tensors
+        device = uvc.device
+        Bt, C, Th, Tw = ctx.tex_shape
+        g = grad_out.to(torch.float32).contiguous()
+        grad_tex = torch.zeros(ctx.tex_shape, dtype=torch.float32, device=device)
+        b = LpBackwardArgs()
+        b.B, b.H, b.W, b.flags = uvc.shape[0], uvc.shape[1], uvc.shape[2], 0
+        b.grad_image, b.uv = _ptr(g), _ptr(uvc)
+        b.C, b.Th, b.Tw, b.interp = C, Th, Tw, _INTERP[ctx.mode]
+        b.grad_texture = _ptr(grad_tex)
+        b.grad_texture_batch_stride = C * Th * Tw if Bt > 1 else 0
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().lp_render_backward(ctypes.byref(b), _stream(device)))
+            launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        return grad_tex, None, None
+
+
+def texture_map(uv, texture_maps, mode="nearest"):
+    return _TextureMap.apply(texture_maps, uv, mode)

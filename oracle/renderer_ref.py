@@ -12,10 +12,10 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import kaolin_shim as kal
+from . import kaolin_shim as _oracle_kal
 
 
-def _look_at_camera(elev, azim, radius, look_at_height):
+def _look_at_camera(elev, azim, radius, look_at_height, kal=_oracle_kal):
     """Camera position on the view sphere and the kaolin look-at matrix.
     reference latent_paint/models/render.py:19-31 and latent_paint_mesh/models/render.py:42-55."""
     x = radius * torch.sin(elev) * torch.sin(azim)
@@ -30,12 +30,31 @@ def _look_at_camera(elev, azim, radius, look_at_height):
     return kal.generate_transformation_matrix(pos, at, up)
 
 
+def _ns(kal):
+    """Accept either this package's flat shim module or a ``kaolin``-shaped module tree (the product's
+    ``kaolin_compat`` — the same glue then runs on the CUDA kernels)."""
+    if kal is None:
+        return _oracle_kal
+    if hasattr(kal, "render"):
+        import types
+        ns = types.SimpleNamespace()
+        for name in ("generate_perspective_projection", "generate_transformation_matrix"):
+            setattr(ns, name, getattr(kal.render.camera, name))
+        for name in ("prepare_vertices", "rasterize", "dibr_rasterization", "texture_mapping", "spherical_harmonic_lighting"):
+            setattr(ns, name, getattr(kal.render.mesh, name))
+        ns.index_vertices_by_faces = kal.ops.mesh.index_vertices_by_faces
+        return ns
+    return kal
+
+
 class LatentPaintRendererRef:
     """Mirror of reference ``src/latent_paint/models/render.py`` (single view, fov π/3)."""
 
-    def __init__(self, dim=(224, 224), interpolation_mode="nearest"):
+    def __init__(self, dim=(224, 224), interpolation_mode="nearest", kal=None, device="cpu"):
         assert interpolation_mode in ["nearest", "bilinear", "bicubic"]        # render.py:9
-        self.camera_projection = kal.generate_perspective_projection(np.pi / 3)  # render.py:11
+        self.kal, self.device = _ns(kal), device
+        kal = self.kal
+        self.camera_projection = kal.generate_perspective_projection(np.pi / 3).to(device)  # render.py:11
         self.interpolation_mode = interpolation_mode
         self.dim = dim
         self.last = {}
@@ -46,8 +65,8 @@ class LatentPaintRendererRef:
 
     def render_single_view(self, vertices, faces, face_attributes, elev=0, azim=0, radius=2, look_at_height=0.0):
         """render.py:34-47 — per-face-vertex colours interpolated by the rasterizer."""
-        dims = self.dim
-        M = self.get_camera_from_view(torch.tensor(elev), torch.tensor(azim), r=radius, look_at_height=look_at_height)
+        dims, kal = self.dim, self.kal
+        M = self.get_camera_from_view(torch.tensor(elev), torch.tensor(azim), r=radius, look_at_height=look_at_height).to(self.device)
         fvc, fvi, _ = kal.prepare_vertices(vertices, faces, self.camera_projection, camera_transform=M)
         feats, face_idx = kal.rasterize(dims[1], dims[0], fvc[:, :, :, -1], fvi, face_attributes)
         mask = (face_idx > -1).float()[..., None]
@@ -57,8 +76,8 @@ class LatentPaintRendererRef:
     def render_single_view_texture(self, verts, faces, uv_face_attr, texture_map, elev=0, azim=0, radius=2,
                                    look_at_height=0.0, dims=None, white_background=False):
         """render.py:50-69."""
-        dims = self.dim if dims is None else dims
-        M = self.get_camera_from_view(torch.tensor(elev), torch.tensor(azim), r=radius, look_at_height=look_at_height)
+        dims, kal = (self.dim if dims is None else dims), self.kal
+        M = self.get_camera_from_view(torch.tensor(elev), torch.tensor(azim), r=radius, look_at_height=look_at_height).to(self.device)
         fvc, fvi, _ = kal.prepare_vertices(verts, faces, self.camera_projection, camera_transform=M)
         uv, face_idx = kal.rasterize(dims[1], dims[0], fvc[:, :, :, -1], fvi, uv_face_attr)
         uv = uv.detach()                                                          # render.py:61
@@ -76,18 +95,20 @@ class LatentPaintMeshRendererRef:
     cameras, DIB-R feature list, SH lighting)."""
 
     def __init__(self, dim=(224, 224), interpolation_mode="nearest",
-                 lights=torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0])):
+                 lights=torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0]), kal=None, device="cpu"):
         assert interpolation_mode in ["nearest", "bilinear", "bicubic"]        # render.py:16
-        self.camera_projection = [kal.generate_perspective_projection(np.pi / 12),   # head, render.py:18
-                                  kal.generate_perspective_projection(np.pi / 4)]    # body, render.py:19
+        self.kal, self.device = _ns(kal), device
+        kal = self.kal
+        self.camera_projection = [kal.generate_perspective_projection(np.pi / 12).to(device),   # head, render.py:18
+                                  kal.generate_perspective_projection(np.pi / 4).to(device)]    # body, render.py:19
         self.look_at_height = torch.tensor([[0.4], [-0.3]])                     # render.py:29-32
         self.interpolation_mode = interpolation_mode
         self.dim = dim
-        self.lights = lights.unsqueeze(0)
+        self.lights = lights.unsqueeze(0).to(device)
         self.last = {}
 
     def get_camera_from_view(self, elev, azim, radius=3.0, look_at_height=0.0):  # render.py:42-55
-        return _look_at_camera(elev, azim, radius, look_at_height)
+        return _look_at_camera(elev, azim, radius, look_at_height, self.kal).to(self.device)
 
     @staticmethod
     def compute_vertex_normals(faces, face_normals, num_vertices=None):
@@ -95,9 +116,10 @@ class LatentPaintMeshRendererRef:
         vertices, divide by the incidence count; NOT re-normalised."""
         V = int(faces.max()) + 1 if num_vertices is None else num_vertices
         B, F = face_normals.shape[0], faces.shape[0]
-        vn = torch.zeros((B, V, 3), dtype=face_normals.dtype)
-        cnt = torch.zeros((B, V), dtype=face_normals.dtype)
-        ones = torch.ones((B, F), dtype=face_normals.dtype)
+        dev = face_normals.device
+        vn = torch.zeros((B, V, 3), dtype=face_normals.dtype, device=dev)
+        cnt = torch.zeros((B, V), dtype=face_normals.dtype, device=dev)
+        ones = torch.ones((B, F), dtype=face_normals.dtype, device=dev)
         for k in range(faces.shape[1]):
             vn.scatter_add_(1, faces[None, :, k:k + 1].repeat(B, 1, 3), face_normals)
             cnt.scatter_add_(1, faces[None, :, k].repeat(B, 1), ones)
@@ -106,7 +128,7 @@ class LatentPaintMeshRendererRef:
     def render_single_view_texture(self, verts, faces, uv_face_attr, texture_map, elev=0, azim=0, radius=2,
                                    look_at_height=0.0, dims=None, white_background=False, disp=None, is_body=True):
         """render.py:160-279.  ``look_at_height`` is ignored exactly as in the reference."""
-        dims = self.dim if dims is None else dims
+        dims, kal = (self.dim if dims is None else dims), self.kal
         if disp is not None:
             verts = verts + disp
         P = 1 if is_body is True else 0
@@ -115,7 +137,7 @@ class LatentPaintMeshRendererRef:
         fvc, fvi, fn = kal.prepare_vertices(verts, faces, self.camera_projection[P], camera_transform=M)
         vn = self.compute_vertex_normals(faces, fn)
         vfn = kal.index_vertices_by_faces(vn, faces)
-        feats = [uv_face_attr.repeat(B, 1, 1, 1), torch.ones((B, faces.shape[0], 3, 1)), vfn]
+        feats = [uv_face_attr.repeat(B, 1, 1, 1), torch.ones((B, faces.shape[0], 3, 1), device=self.device), vfn]
         (uv, mask, normals), _soft, face_idx = kal.dibr_rasterization(
             dims[1], dims[0], fvc[:, :, :, -1], fvi, feats, abs(fn[:, :, -1]), rast_backend="cuda")
         image = kal.texture_mapping(uv, texture_map.repeat(B, 1, 1, 1), mode="bilinear")   # render.py:243

@@ -139,3 +139,39 @@ def test_shard_views():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_views(4, 4, 4)
+
+
+def test_kaolin_compat_surface_and_install():
+    """Every kaolin attribute the reference's render path touches exists in the compat tree."""
+    import sys
+    kc = lp.kaolin_compat.make_module()
+    for path in ["render.camera.generate_perspective_projection", "render.camera.generate_transformation_matrix",
+                 "render.mesh.prepare_vertices", "render.mesh.rasterize", "render.mesh.dibr_rasterization",
+                 "render.mesh.texture_mapping", "render.mesh.spherical_harmonic_lighting",
+                 "ops.mesh.index_vertices_by_faces", "ops.mesh.uniform_laplacian", "io.obj.import_mesh"]:
+        obj = kc
+        for part in path.split("."):
+            obj = getattr(obj, part)
+        assert callable(obj), path
+    # small ops agree with the oracle on CPU (the heavy ones need the GPU)
+    v = torch.randn(5, 3, generator=torch.Generator().manual_seed(0))
+    f = torch.tensor([[0, 1, 2], [2, 3, 4]])
+    M = camera.camera_from_view(torch.tensor(1.0), torch.tensor(0.5), 1.5, 0.1)
+    proj = camera.generate_perspective_projection(np.pi / 3)
+    a = kc.render.mesh.prepare_vertices(v, f, proj, camera_transform=M)
+    b = kal.prepare_vertices(v, f, proj, camera_transform=M)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    n = torch.randn(1, 4, 4, 3, generator=torch.Generator().manual_seed(1))
+    L = torch.tensor([[1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0]])
+    assert torch.equal(kc.render.mesh.spherical_harmonic_lighting(n, L), kal.spherical_harmonic_lighting(n, L))
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "kaolin" or k.startswith("kaolin.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        lp.kaolin_compat.install()
+        import kaolin as kk
+        assert kk.render.mesh.rasterize is lp.kaolin_compat.rasterize
+    finally:
+        for k in [k for k in sys.modules if k == "kaolin" or k.startswith("kaolin.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
