@@ -68,6 +68,11 @@ def load_scene(w):
     return verts, m.faces, lp.meshio.face_uv_attributes(m)
 
 
+def render_forward_raster_fused(fwd, stream):
+    """Tile rasterizer with the texture fetch fused (lp_render_forward minus lp_render_prepare)."""
+    return _lib.lib().lp_render_raster_shade(ctypes.byref(fwd), stream)
+
+
 class DeviceStep:
     """One buffer set + the two C-ABI argument blocks of a fwd+bwd step on resident inputs."""
 
@@ -119,6 +124,32 @@ class DeviceStep:
         self.fwd, self.bwd = a, b
         self.keep = (verts, faces, uv)
         self.launches = 0
+
+    def prepare(self, stream, with_raster):
+        """The texture-independent stages of this set's views on `stream` (a raw cudaStream_t handle):
+        geometry + bins, and with `with_raster` also visibility / uv / mask."""
+        L = _lib.lib()
+        _lib.check(L.lp_render_prepare(ctypes.byref(self.fwd), stream))
+        n = L.lp_last_launch_count()
+        if with_raster:
+            _lib.check(L.lp_render_raster(ctypes.byref(self.fwd), stream))
+            n += L.lp_last_launch_count()
+        self.launches_prepare = n
+
+    def shade_backward(self, stream, torch_stream, with_raster):
+        """The rest of the step: (tile rasterizer fused with the texture fetch | texture fetch only), then
+        zero the gradient and scatter the upstream gradient into it."""
+        L = _lib.lib()
+        if with_raster:
+            _lib.check(L.lp_render_shade(ctypes.byref(self.fwd), stream))
+        else:
+            _lib.check(render_forward_raster_fused(self.fwd, stream))
+        n = L.lp_last_launch_count()
+        if not self.accum.numel():
+            with torch.cuda.stream(torch_stream):
+                self.grad_tex.zero_()
+        _lib.check(L.lp_render_backward(ctypes.byref(self.bwd), stream))
+        self.launches = self.launches_prepare + n + L.lp_last_launch_count()
 
     def run(self):
         """Enqueue forward, zero the gradient, backward on torch's current stream."""
@@ -249,6 +280,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster"],
+                    help="overlap texture-independent stages of step k+1 with step k on a second stream: 'geometry' = setup + "
+                         "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1); auto = geometry at N=1, raster at N>1")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--cpu-views", type=int, default=40, help="views timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
@@ -298,10 +332,61 @@ def main():
             except Exception as exc:                      # eager launches still measure the same kernels
                 print(f"bench.py: CUDA graph capture failed ({exc}); timing eager launches", file=sys.stderr)
                 graphs = None
-    launches_per_step = sets[0].launches
+
+    # --pipeline: the texture-independent stages of the next step (geometry, bins, visibility, uv) run on a
+    # second stream while the current step fetches the texture, back-propagates (and all-reduces); each
+    # buffer set has its own workspace and saved-uv buffer
+    if args.pipeline == "auto":
+        args.pipeline = "geometry" if world == 1 else "raster"
+    pipe_raster = args.pipeline == "raster"
+    args.pipeline = None if args.pipeline == "off" else args.pipeline
+    prep_stream = torch.cuda.Stream(device) if args.pipeline else None
+    prep_done = [torch.cuda.Event() for _ in sets]
+    set_free = [torch.cuda.Event() for _ in sets]
+    pipe_state = {"primed": [False] * len(sets)}
+    h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if args.pipeline else None
+    h_main = ctypes.c_void_p(stream.cuda_stream)
+
+    def pipelined_step(i):
+        k = i % len(sets)
+        if pipe_state["primed"][k]:
+            prep_stream.wait_event(set_free[k])          # the workspace of set k is free again
+        sets[k].prepare(h_prep, pipe_raster)
+        prep_done[k].record(prep_stream)
+        stream.wait_event(prep_done[k])
+        sets[k].shade_backward(h_main, stream, pipe_raster)
+        set_free[k].record(stream)
+        pipe_state["primed"][k] = True
+        return k
+
+    # the same pipeline captured once as a CUDA graph of PIPE_STEPS steps (two capture streams, event edges)
+    PIPE_STEPS = 2 * len(sets)
+    pipe_graph = None
+    if args.pipeline and not args.no_graph:
+        try:
+            with torch.cuda.stream(stream):
+                for i in range(PIPE_STEPS):                     # warm both paths before capture
+                    pipelined_step(i)
+                stream.wait_stream(prep_stream)
+                torch.cuda.synchronize(device)
+                pipe_state["primed"] = [False] * len(sets)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    prep_stream.wait_stream(stream)
+                    for i in range(PIPE_STEPS):
+                        pipelined_step(i)
+                    stream.wait_stream(prep_stream)
+                pipe_graph = g
+                pipe_state["primed"] = [False] * len(sets)
+        except Exception as exc:
+            print(f"bench.py: pipelined graph capture failed ({exc}); running the pipeline eagerly", file=sys.stderr)
+            pipe_graph = None
+            pipe_state["primed"] = [False] * len(sets)
 
     def local_step(i):
         k = i % len(sets)
+        if args.pipeline:
+            return pipelined_step(i)
         if graphs is not None:
             graphs[k].replay()
         else:
@@ -327,8 +412,18 @@ def main():
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(args.steps):
-            one_step(i)
+        if args.pipeline:
+            prep_stream.wait_event(e0)
+        if pipe_graph is not None and world == 1:
+            for _ in range(args.steps // PIPE_STEPS):
+                pipe_graph.replay()
+            for i in range(args.steps % PIPE_STEPS):
+                one_step(i)
+        else:
+            for i in range(args.steps):
+                one_step(i)
+        if args.pipeline:
+            stream.wait_stream(prep_stream)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -407,10 +502,11 @@ def main():
             cpu = {"value": vps, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"{args.cpu_views} views of the same workload, one view per call, {dt:.1f} s; oracle torch CPU path"}
 
+        launches_per_step = sets[0].launches
         line = {"metric": "views/sec (fwd+bwd render)", "value": value, "unit": "views/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w["label"], "views_per_gpu_per_step": B, "cuda_graph": graphs is not None,
+                "config": {"workload": w["label"], "views_per_gpu_per_step": B, "cuda_graph": (graphs is not None and not args.pipeline) or pipe_graph is not None, "pipeline": args.pipeline or "off",
                            "l2": f"{len(sets)} rotating buffer sets of {set_bytes / 1e6:.0f} MB each "
                                  f"({len(sets) * set_bytes / 1e6:.0f} MB > 126 MB L2): inputs larger than L2",
                            "parallelism": f"views sharded over {world} GPU(s)" + (", NCCL all-reduce of the texture gradient each step" if world > 1 else "")},

@@ -165,6 +165,17 @@ int lp_cameras_from_views(const float *elev, const float *azim, const float *rad
 uint64_t    lp_backward_workspace_bytes(int32_t C, int32_t Th, int32_t Tw);
 
 int lp_render_forward(const LpForwardArgs *args, void *stream);
+/* lp_render_forward split in three, so a caller can overlap everything that does not read the texture
+ * (geometry, binning, visibility, uv / mask / normals) of the NEXT batch with the texture fetch, the backward and
+ * the gradient all-reduce of the current one on another stream:
+ *   lp_render_prepare  stage 1 + binning                      (needs verts / cameras, fills the workspace)
+ *   lp_render_raster   stage 2-3: visibility, uv, mask, optional buffers  (needs the prepared workspace)
+ *   lp_render_shade    stage 4: texture fetch + composition -> image     (needs uv [, mask, tile_any] of the raster call)
+ * All three take the same argument block as lp_render_forward, which runs 1-4 with the fetch fused into the tile kernel. */
+int lp_render_prepare(const LpForwardArgs *args, void *stream);
+int lp_render_raster(const LpForwardArgs *args, void *stream);
+int lp_render_shade(const LpForwardArgs *args, void *stream);
+int lp_render_raster_shade(const LpForwardArgs *args, void *stream);   /* raster + shade in the one fused tile kernel */
 int lp_render_backward(const LpBackwardArgs *args, void *stream);
 int lp_texture_map_forward(const LpTextureMapArgs *args, void *stream);
 

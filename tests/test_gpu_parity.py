@@ -396,3 +396,31 @@ def test_kaolin_compat_runs_the_reference_glue_on_the_kernels():
     for a, b, k in zip(og, oc, ("image", "mask", "normals", "lighting")):
         assert_close(a, b, k)
     assert_close(tg.grad, tc.grad, "grad_texture (mesh flavour)", rtol=1e-4, atol=1e-4)
+
+
+def test_split_forward_equals_fused_forward():
+    """lp_render_prepare + lp_render_raster + lp_render_shade (the pipelined form bench.py overlaps across
+    steps) must give exactly the buffers of the fused lp_render_forward."""
+    from bench import DeviceStep, WORKLOADS, cameras_for, make_views
+    L = _lib.lib()
+    for flavour_white in (False, True):
+        w = dict(WORKLOADS["c2"], B=2, H=160, W=208, T=256)
+        verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
+        geom = (verts.to(DEV).float().contiguous(), faces.to(DEV, torch.int32).contiguous(),
+                uv.to(DEV).float().reshape(-1, 3, 2).contiguous())
+        radius, theta, phi = make_views(w["B"], 5)
+        cams = cameras_for(radius, theta, phi, w["dy"])
+        a, b_ = DeviceStep(geom, w, cams, 1, torch.device(DEV)), DeviceStep(geom, w, cams, 1, torch.device(DEV))
+        if flavour_white:
+            for st in (a, b_):
+                st.fwd.flags |= _lib.LP_FLAG_WHITE_BACKGROUND
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(L.lp_render_forward(ctypes.byref(a.fwd), stream))
+        b_.image.fill_(-7.0)
+        for fn in (L.lp_render_prepare, L.lp_render_raster, L.lp_render_shade):
+            _lib.check(fn(ctypes.byref(b_.fwd), stream))
+        torch.cuda.synchronize()
+        assert torch.equal(a.image, b_.image) and torch.equal(a.mask, b_.mask) and torch.equal(a.tile_any, b_.tile_any)
+        live = a.tile_any.bool().repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :w["H"], :w["W"]]
+        assert torch.equal(a.uv[live], b_.uv[live])
+        assert float(a.mask.sum()) > 0
