@@ -76,7 +76,7 @@ def render_forward_raster_fused(fwd, stream):
 class DeviceStep:
     """One buffer set + the two C-ABI argument blocks of a fwd+bwd step on resident inputs."""
 
-    def __init__(self, geom, w, cams, seed, device):
+    def __init__(self, geom, w, cams, seed, device, grad_tex=None):
         verts, faces, uv = geom
         B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
         self.device = device
@@ -86,7 +86,7 @@ class DeviceStep:
         self.image = torch.empty(B, C, H, W, device=device)
         self.mask = torch.empty(B, 1, H, W, device=device)
         self.uv = torch.empty(B, H, W, 2, device=device)
-        self.grad_tex = torch.zeros(C, T, T, device=device)
+        self.grad_tex = torch.zeros(C, T, T, device=device) if grad_tex is None else grad_tex
         self.tile_any = torch.empty(B, (H + 15) // 16, (W + 15) // 16, dtype=torch.uint8, device=device)
         L = _lib.lib()
         self.ws = torch.empty(int(L.lp_workspace_bytes(B, faces.shape[0], H, W)), dtype=torch.uint8, device=device)
@@ -283,6 +283,9 @@ def main():
     ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster"],
                     help="overlap texture-independent stages of step k+1 with step k on a second stream: 'geometry' = setup + "
                          "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1); auto = geometry at N=1, raster at N>1")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
+                    help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
+                         "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--cpu-views", type=int, default=40, help="views timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
@@ -308,10 +311,38 @@ def main():
             uv.to(device).float().reshape(-1, 3, 2).contiguous())
     B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
     V, F = verts.shape[0], faces.shape[0]
-    sets = []
+    sets, symm_bufs, allreduce_mode = [], [], "none" if world == 1 else "nccl"
+    if args.allreduce == "auto":        # measured: NCCL wins at 2 GPUs, the in-switch kernel from 4 GPUs up
+        args.allreduce = "multimem" if world >= 4 else "nccl"
+        auto_allreduce = True
+    else:
+        auto_allreduce = False
+    if world > 1 and args.allreduce != "nccl":
+        try:
+            from latent_nerf_test_b200.parallel import SymmetricGradientBuffer
+            for s in range(args.sets):
+                sb = SymmetricGradientBuffer(C * T * T, device)
+                if args.allreduce == "p2p":
+                    sb.mode = "p2p"
+                elif args.allreduce == "multimem" and sb.mode != "multimem":
+                    raise RuntimeError("no multicast support on this box" + (" (auto: using NCCL)" if auto_allreduce else ""))
+                symm_bufs.append(sb)
+            # self-check against NCCL once: same sum within fp32 tolerance
+            probe = torch.randn(C * T * T, device=device, generator=torch.Generator(device=device).manual_seed(rank))
+            symm_bufs[0].flat[:probe.numel()].copy_(probe)
+            symm_bufs[0].all_reduce()
+            dist.all_reduce(probe)
+            torch.cuda.synchronize(device)
+            if not torch.allclose(symm_bufs[0].flat[:probe.numel()], probe, rtol=1e-5, atol=1e-5):
+                raise RuntimeError("symmetric-memory all-reduce disagrees with NCCL")
+            allreduce_mode = symm_bufs[0].mode
+        except Exception as exc:
+            print(f"bench.py: falling back to NCCL all-reduce ({exc})", file=sys.stderr)
+            symm_bufs, allreduce_mode = [], "nccl"
     for s in range(args.sets):
         radius, theta, phi = make_views(B, 1000 * rank + s)
-        sets.append(DeviceStep(geom, w, cameras_for(radius, theta, phi, w["dy"]), 10 * s + 1, device))
+        gt = symm_bufs[s].view((C, T, T)) if symm_bufs else None
+        sets.append(DeviceStep(geom, w, cameras_for(radius, theta, phi, w["dy"]), 10 * s + 1, device, grad_tex=gt))
     set_bytes = sum(t.numel() * t.element_size() for t in (sets[0].tex, sets[0].grad_image, sets[0].image, sets[0].mask,
                                                            sets[0].uv, sets[0].grad_tex))
 
@@ -347,7 +378,15 @@ def main():
     h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if args.pipeline else None
     h_main = ctypes.c_void_p(stream.cuda_stream)
 
-    def pipelined_step(i):
+    def exchange(k):
+        """The path's one exchange step: sum the texture gradient of set k over the ranks (main stream)."""
+        if world > 1:
+            if symm_bufs:
+                symm_bufs[k].all_reduce()
+            else:
+                dist.all_reduce(sets[k].grad_tex)
+
+    def pipelined_step(i, with_exchange=True):
         k = i % len(sets)
         if pipe_state["primed"][k]:
             prep_stream.wait_event(set_free[k])          # the workspace of set k is free again
@@ -355,6 +394,8 @@ def main():
         prep_done[k].record(prep_stream)
         stream.wait_event(prep_done[k])
         sets[k].shade_backward(h_main, stream, pipe_raster)
+        if with_exchange:
+            exchange(k)
         set_free[k].record(stream)
         pipe_state["primed"][k] = True
         return k
@@ -362,7 +403,7 @@ def main():
     # the same pipeline captured once as a CUDA graph of PIPE_STEPS steps (two capture streams, event edges)
     PIPE_STEPS = 2 * len(sets)
     pipe_graph = None
-    if args.pipeline and not args.no_graph:
+    if args.pipeline and not args.no_graph and (world == 1 or symm_bufs):
         try:
             with torch.cuda.stream(stream):
                 for i in range(PIPE_STEPS):                     # warm both paths before capture
@@ -384,9 +425,10 @@ def main():
             pipe_state["primed"] = [False] * len(sets)
 
     def local_step(i):
+        """One step without the exchange (rank-local keep-busy loop)."""
         k = i % len(sets)
         if args.pipeline:
-            return pipelined_step(i)
+            return pipelined_step(i, with_exchange=False)
         if graphs is not None:
             graphs[k].replay()
         else:
@@ -394,9 +436,10 @@ def main():
         return k
 
     def one_step(i):
-        k = local_step(i)
-        if world > 1:                      # the path's one exchange: sum the texture gradient over the ranks
-            dist.all_reduce(sets[k].grad_tex)
+        if args.pipeline:
+            pipelined_step(i)
+        else:
+            exchange(local_step(i))
 
     def barrier():
         if world > 1:
@@ -414,7 +457,7 @@ def main():
         e0.record(stream)
         if args.pipeline:
             prep_stream.wait_event(e0)
-        if pipe_graph is not None and world == 1:
+        if pipe_graph is not None:
             for _ in range(args.steps // PIPE_STEPS):
                 pipe_graph.replay()
             for i in range(args.steps % PIPE_STEPS):
@@ -509,7 +552,7 @@ def main():
                 "config": {"workload": w["label"], "views_per_gpu_per_step": B, "cuda_graph": (graphs is not None and not args.pipeline) or pipe_graph is not None, "pipeline": args.pipeline or "off",
                            "l2": f"{len(sets)} rotating buffer sets of {set_bytes / 1e6:.0f} MB each "
                                  f"({len(sets) * set_bytes / 1e6:.0f} MB > 126 MB L2): inputs larger than L2",
-                           "parallelism": f"views sharded over {world} GPU(s)" + (", NCCL all-reduce of the texture gradient each step" if world > 1 else "")},
+                           "parallelism": f"views sharded over {world} GPU(s)" + (f", all-reduce of the texture gradient each step ({allreduce_mode})" if world > 1 else "")},
                 "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

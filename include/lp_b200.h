@@ -192,6 +192,16 @@ int lp_render_step_host(const LpForwardArgs *fwd, const LpBackwardArgs *bwd,
                         const float *cameras_host, const float *grad_image_host,
                         float *image_host, float *mask_host, float *grad_texture_host, void *stream);
 
+/* The path's one exchange step (SURVEY.md §8 e): sum the flat texture-gradient buffer over the ranks of one box.
+ * The buffer of every rank must live in symmetric memory (same size, mapped into every peer); the caller puts a
+ * stream-ordered barrier over all ranks BEFORE (every rank's backward finished) and AFTER each call (and between
+ * the two phases of the p2p form).  count = number of floats, a multiple of 4.
+ *   lp_allreduce_multimem  NVSwitch in-switch reduction (multimem.ld_reduce / multimem.st on the multicast address)
+ *   lp_allreduce_p2p       phase 0 reduce-scatter, phase 1 all-gather over plain peer pointers (device array of
+ *                          `world` buffer pointers) — fallback when the box has no multicast support */
+int lp_allreduce_multimem(void *multicast_ptr, int64_t count, int32_t rank, int32_t world, void *stream);
+int lp_allreduce_p2p(void *const *buffer_ptrs_dev, int64_t count, int32_t rank, int32_t world, int32_t phase, void *stream);
+
 /* Instrumentation (bench.py's roofline leg): while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  lp_timing_collect waits for them, sums the elapsed
  * milliseconds per kernel name into total_ms[]/counts[] (names[] receives static strings), clears

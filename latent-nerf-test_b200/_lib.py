@@ -32,7 +32,7 @@ LP_FLAG_GRAD_OVERWRITE = 1 << 5
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p"]
 
 
 class LpForwardArgs(Structure):
@@ -119,6 +119,10 @@ def lib() -> ctypes.CDLL:
     for name in ("lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade"):
         getattr(L, name).restype = c_int32
         getattr(L, name).argtypes = [POINTER(LpForwardArgs), c_void_p]
+    L.lp_allreduce_multimem.restype = c_int32
+    L.lp_allreduce_multimem.argtypes = [c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p]
+    L.lp_allreduce_p2p.restype = c_int32
+    L.lp_allreduce_p2p.argtypes = [c_void_p, ctypes.c_int64, c_int32, c_int32, c_int32, c_void_p]
     L.lp_render_backward.restype = c_int32
     L.lp_render_backward.argtypes = [POINTER(LpBackwardArgs), c_void_p]
     L.lp_texture_map_forward.restype = c_int32

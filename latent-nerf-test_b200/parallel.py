@@ -63,3 +63,52 @@ def render_views_sharded(render_fn, view_params: dict, num_views: int, group=Non
     shard = {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == num_views else v)
              for k, v in view_params.items()}
     return render_fn(**shard), (lo, hi)
+
+
+class SymmetricGradientBuffer:
+    """Flat fp32 gradient buffer in symmetric memory + the library's own all-reduce kernels over NVLink /
+    NVSwitch peer memory (``lp_allreduce_multimem`` — in-switch reduction — or the two-shot
+    ``lp_allreduce_p2p``).  ``torch.distributed._symmetric_memory`` is the plumbing: allocation, rendezvous
+    (peer / multicast mappings) and the stream-ordered barriers around the kernels.
+
+    ``flat[:numel]`` is the payload; the tail pads the length to a multiple of ``4 * world`` floats so every
+    rank owns an equally sized, 16-byte aligned slice.
+    """
+
+    def __init__(self, numel: int, device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+        self._lib, self._ctypes = _lib, ctypes
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        quantum = 4 * self.world
+        self.numel = numel
+        self.padded = (numel + quantum - 1) // quantum * quantum
+        self.flat = symm.empty(self.padded, dtype=torch.float32, device=device)
+        self.flat.zero_()
+        self.handle = symm.rendezvous(self.flat, self.group.group_name)
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.mode = "multimem" if self.multicast_ptr else "p2p"
+
+    def view(self, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return self.flat[:n].view(shape)
+
+    def all_reduce(self):
+        """Sum over the ranks, in place, on torch's current stream."""
+        L, c = self._lib.lib(), self._ctypes
+        stream = c.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        self.handle.barrier(channel=0)                       # every rank's backward has finished
+        if self.mode == "multimem":
+            self._lib.check(L.lp_allreduce_multimem(c.c_void_p(self.multicast_ptr), self.padded, self.rank, self.world, stream))
+        else:
+            ptrs = c.c_void_p(self.handle.buffer_ptrs_dev)
+            self._lib.check(L.lp_allreduce_p2p(ptrs, self.padded, self.rank, self.world, 0, stream))
+            self.handle.barrier(channel=1)                   # all slices reduced
+            self._lib.check(L.lp_allreduce_p2p(ptrs, self.padded, self.rank, self.world, 1, stream))
+        self.handle.barrier(channel=2)                       # every rank holds the full sum; peers are done reading

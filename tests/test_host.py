@@ -23,7 +23,7 @@ HEADER = os.path.join(ROOT, "include", "lp_b200.h")
 def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     src = open(HEADER).read()
-    declared = sorted(set(re.findall(r"\b(lp_[a-z_]+)\s*\(", src)))
+    declared = sorted(set(re.findall(r"\b(lp_[a-z0-9_]+)\s*\(", src)))
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/lp_b200.h but not exported"
