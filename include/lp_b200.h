@@ -210,6 +210,13 @@ int lp_allreduce_p2p(void *const *buffer_ptrs_dev, int64_t count, int32_t rank, 
 int lp_timing_enable(int on);
 int lp_timing_collect(int max_names, const char **names, float *total_ms, int *counts);
 
+/* Same, without the final synchronisation: with pinned host buffers the copies are asynchronous, so steps issued
+ * on different streams overlap their host->device copy, kernels and device->host copy (full-duplex PCIe).  The host
+ * results are valid once the stream has been synchronised. */
+int lp_render_step_host_async(const LpForwardArgs *fwd, const LpBackwardArgs *bwd,
+                              const float *cameras_host, const float *grad_image_host,
+                              float *image_host, float *mask_host, float *grad_texture_host, void *stream);
+
 /* number of kernel launches the last lp_render_forward / lp_render_backward on this thread enqueued */
 int lp_last_launch_count(void);
 

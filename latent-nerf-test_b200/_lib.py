@@ -32,7 +32,7 @@ LP_FLAG_GRAD_OVERWRITE = 1 << 5
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_render_step_host_async"]
 
 
 class LpForwardArgs(Structure):
@@ -132,6 +132,8 @@ def lib() -> ctypes.CDLL:
     L.lp_render_step_host.restype = c_int32
     L.lp_render_step_host.argtypes = [POINTER(LpForwardArgs), POINTER(LpBackwardArgs), c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]
+    L.lp_render_step_host_async.restype = c_int32
+    L.lp_render_step_host_async.argtypes = L.lp_render_step_host.argtypes
     L.lp_last_launch_count.restype = c_int32
     L.lp_timing_enable.restype = c_int32
     L.lp_timing_enable.argtypes = [c_int32]
