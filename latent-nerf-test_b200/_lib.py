@@ -102,7 +102,7 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = build()
+    path = os.environ.get("LP_B200_LIB") or build()      # LP_B200_LIB: load a specific build (kernel A/B experiments)
     L = ctypes.CDLL(path)
     L.lp_version.restype = c_int32
     L.lp_last_error.restype = c_char_p
