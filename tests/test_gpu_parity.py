@@ -424,3 +424,32 @@ def test_split_forward_equals_fused_forward():
         live = a.tile_any.bool().repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :w["H"], :w["W"]]
         assert torch.equal(a.uv[live], b_.uv[live])
         assert float(a.mask.sum()) > 0
+
+
+def test_random_scenes_visibility_bit_exact():
+    """Seeded sweep over meshes, odd resolutions, camera distances (including cameras close enough that faces
+    straddle the image plane) and both flavours: the visibility buffer must equal the oracle's bit for bit."""
+    g = torch.Generator().manual_seed(1234)
+    meshes = {name: scene(name, 0.6, 0.25) for name in ("sphere", "blub", "teddy", "nascar")}
+    tex = rnd((1, 3, 37, 53), 1).to(DEV)                     # non-square, non-power-of-two texture
+    checked = 0
+    for it in range(24):
+        name = list(meshes)[it % len(meshes)]
+        verts, faces, uv = meshes[name]
+        W = int(torch.randint(8, 200, (1,), generator=g)); H = int(torch.randint(8, 200, (1,), generator=g))
+        elev = float(torch.rand(1, generator=g) * 2.6 + 0.25); azim = float(torch.rand(1, generator=g) * 6.28)
+        radius = float(torch.rand(1, generator=g) * 1.4 + (0.45 if it % 6 == 5 else 0.9))   # 0.45: inside the mesh's bounding sphere
+        mode = "bilinear" if it % 2 else "nearest"
+        r = lp.LatentPaintRenderer(DEV, dim=(W, H), interpolation_mode=mode)
+        r.keep_buffers = True
+        image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, elev=elev, azim=azim,
+                                                   radius=radius, look_at_height=0.25, white_background=bool(it % 3 == 0))
+        ref = renderer_ref.LatentPaintRendererRef(dim=(W, H), interpolation_mode=mode)
+        oi, om = ref.render_single_view_texture(verts, faces, uv, tex.cpu(), elev=elev, azim=azim, radius=radius,
+                                                look_at_height=0.25, white_background=bool(it % 3 == 0))
+        assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ref.last["face_idx"]), (it, name, W, H, radius)
+        assert torch.equal(mask.cpu(), om), (it, name)
+        if mode == "bilinear":                                # nearest on a non-power-of-two texture may flip exact ties (DESIGN.md)
+            assert_close(image, oi, f"image {it}")
+        checked += int((ref.last["face_idx"] >= 0).sum())
+    assert checked > 10000
