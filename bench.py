@@ -112,7 +112,7 @@ class DeviceStep:
         b.grad_texture = self.grad_tex.data_ptr()
         b.tile_any = self.tile_any.data_ptr()
         self.accum = torch.empty(int(L.lp_backward_workspace_bytes(C, T, T)), dtype=torch.uint8, device=device)
-        if self.accum.numel() and os.environ.get("LP_BWD_VEC", "0") == "1":
+        if self.accum.numel() and os.environ.get("LP_BWD_VEC", "1") == "1":
             b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
             b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
         else:
