@@ -320,8 +320,8 @@ def main():
     B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
     V, F = verts.shape[0], faces.shape[0]
     sets, symm_bufs, allreduce_mode = [], [], "none" if world == 1 else "nccl"
-    if args.allreduce == "auto":        # measured: NCCL wins at 2 GPUs, the in-switch kernel from 4 GPUs up
-        args.allreduce = "multimem" if world >= 4 else "nccl"
+    if args.allreduce == "auto":        # measured: inside the step graph the two-shot peer kernels win at
+        args.allreduce = "multimem" if world >= 4 else "p2p"      # 2 GPUs, the in-switch kernel from 4 GPUs up
         auto_allreduce = True
     else:
         auto_allreduce = False
