@@ -64,6 +64,7 @@ enum {
                                            (Renderer.render_single_view, latent_paint render.py:34-47) */
     LP_FLAG_GRAD_OVERWRITE   = 1u << 5  /* lp_render_backward with a workspace: grad_texture is written, not
                                            accumulated into, so the caller need not zero it */
+    /* bits 24-30 are profiling switches of bench.py (stop-after-stage ablations), not part of the contract */
 };
 
 typedef struct LpForwardArgs {
