@@ -130,11 +130,15 @@ class DeviceStep:
         geometry + bins, and with `with_raster` also visibility / uv / mask."""
         L = _lib.lib()
         _lib.check(L.lp_render_prepare(ctypes.byref(self.fwd), stream))
-        n = L.lp_last_launch_count()
+        self.launches_prepare = L.lp_last_launch_count()
         if with_raster:
-            _lib.check(L.lp_render_raster(ctypes.byref(self.fwd), stream))
-            n += L.lp_last_launch_count()
-        self.launches_prepare = n
+            self.raster(stream)
+
+    def raster(self, stream):
+        """Visibility / uv / mask of this set's views (no texture access) on `stream`; needs prepare()."""
+        L = _lib.lib()
+        _lib.check(L.lp_render_raster(ctypes.byref(self.fwd), stream))
+        self.launches_prepare += L.lp_last_launch_count()
 
     def shade_backward(self, stream, torch_stream, with_raster):
         """The rest of the step: (tile rasterizer fused with the texture fetch | texture fetch only), then
@@ -288,9 +292,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster"],
-                    help="overlap texture-independent stages of step k+1 with step k on a second stream: 'geometry' = setup + "
-                         "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1); auto = geometry at N=1, raster at N>1")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster", "deep"],
+                    help="overlap texture-independent stages of later steps with step k on other streams: 'geometry' = setup + "
+                         "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1), 'deep' = three stages on three "
+                         "streams (geometry | visibility/uv | texture fetch + backward + exchange); auto = geometry at N=1, raster at N>1")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
                     help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
                          "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
@@ -377,13 +382,17 @@ def main():
     # buffer set has its own workspace and saved-uv buffer
     if args.pipeline == "auto":
         args.pipeline = "geometry" if world == 1 else "raster"
-    pipe_raster = args.pipeline == "raster"
+    pipe_deep = args.pipeline == "deep"
+    pipe_raster = args.pipeline == "raster" or pipe_deep
     args.pipeline = None if args.pipeline == "off" else args.pipeline
     prep_stream = torch.cuda.Stream(device) if args.pipeline else None
+    rast_stream = torch.cuda.Stream(device) if pipe_deep else None
+    geom_done = [torch.cuda.Event() for _ in sets]
     prep_done = [torch.cuda.Event() for _ in sets]
     set_free = [torch.cuda.Event() for _ in sets]
     pipe_state = {"primed": [False] * len(sets)}
     h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if args.pipeline else None
+    h_rast = ctypes.c_void_p(rast_stream.cuda_stream) if pipe_deep else None
     h_main = ctypes.c_void_p(stream.cuda_stream)
 
     def exchange(k):
@@ -398,8 +407,15 @@ def main():
         k = i % len(sets)
         if pipe_state["primed"][k]:
             prep_stream.wait_event(set_free[k])          # the workspace of set k is free again
-        sets[k].prepare(h_prep, pipe_raster)
-        prep_done[k].record(prep_stream)
+        if pipe_deep:
+            sets[k].prepare(h_prep, False)
+            geom_done[k].record(prep_stream)
+            rast_stream.wait_event(geom_done[k])
+            sets[k].raster(h_rast)
+            prep_done[k].record(rast_stream)
+        else:
+            sets[k].prepare(h_prep, pipe_raster)
+            prep_done[k].record(prep_stream)
         stream.wait_event(prep_done[k])
         sets[k].shade_backward(h_main, stream, pipe_raster)
         if with_exchange:
@@ -409,7 +425,10 @@ def main():
         return k
 
     # the same pipeline captured once as a CUDA graph of PIPE_STEPS steps (two capture streams, event edges)
-    PIPE_STEPS = 2 * len(sets)
+    # one replay = PIPE_STEPS steps; the pipeline drains between replays, so a replay is made long
+    PIPE_STEPS = len(sets) * max(2, min(10, args.steps // len(sets)))
+    if os.environ.get("LP_PIPE_STEPS"):
+        PIPE_STEPS = len(sets) * max(1, int(os.environ["LP_PIPE_STEPS"]) // len(sets))
     pipe_graph = None
     if args.pipeline and not args.no_graph and (world == 1 or symm_bufs):
         try:
@@ -422,9 +441,13 @@ def main():
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
                     prep_stream.wait_stream(stream)
+                    if pipe_deep:
+                        rast_stream.wait_stream(stream)
                     for i in range(PIPE_STEPS):
                         pipelined_step(i)
                     stream.wait_stream(prep_stream)
+                    if pipe_deep:
+                        stream.wait_stream(rast_stream)
                 pipe_graph = g
                 pipe_state["primed"] = [False] * len(sets)
         except Exception as exc:
@@ -465,6 +488,8 @@ def main():
         e0.record(stream)
         if args.pipeline:
             prep_stream.wait_event(e0)
+        if pipe_deep:
+            rast_stream.wait_event(e0)
         if pipe_graph is not None:
             for _ in range(args.steps // PIPE_STEPS):
                 pipe_graph.replay()
@@ -475,6 +500,8 @@ def main():
                 one_step(i)
         if args.pipeline:
             stream.wait_stream(prep_stream)
+        if pipe_deep:
+            stream.wait_stream(rast_stream)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

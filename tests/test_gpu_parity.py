@@ -403,8 +403,10 @@ def test_split_forward_equals_fused_forward():
     steps) must give exactly the buffers of the fused lp_render_forward."""
     from bench import DeviceStep, WORKLOADS, cameras_for, make_views
     L = _lib.lib()
-    for flavour_white in (False, True):
-        w = dict(WORKLOADS["c2"], B=2, H=160, W=208, T=256)
+    # W % 4 == 0 takes the four-pixels-per-thread texture-fetch kernel, W = 202 the one-pixel one
+    for flavour_white, interp, width in ((False, "bilinear", 208), (True, "bilinear", 208), (False, "nearest", 208),
+                                         (True, "bilinear", 202), (False, "nearest", 202)):
+        w = dict(WORKLOADS["c2"], B=2, H=160, W=width, T=256, interp=interp)
         verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
         geom = (verts.to(DEV).float().contiguous(), faces.to(DEV, torch.int32).contiguous(),
                 uv.to(DEV).float().reshape(-1, 3, 2).contiguous())
