@@ -308,7 +308,7 @@ def test_c_abi_error_codes_on_device():
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_UNSUPPORTED
     a.interp = 0
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_OK
-    assert L.lp_last_launch_count() == 3
+    assert L.lp_last_launch_count() == 4        # setup, scan, fill, tile kernel
     torch.cuda.synchronize()
     assert float(mask.sum()) > 0
     r = lp.LatentPaintRenderer(DEV, dim=(32, 32), interpolation_mode="bicubic")
