@@ -76,7 +76,7 @@ def render_forward_raster_fused(fwd, stream):
 class DeviceStep:
     """One buffer set + the two C-ABI argument blocks of a fwd+bwd step on resident inputs."""
 
-    def __init__(self, geom, w, cams, seed, device, grad_tex=None):
+    def __init__(self, geom, w, cams, seed, device, grad_tex=None, accum=None):
         verts, faces, uv = geom
         B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
         self.device = device
@@ -111,8 +111,17 @@ class DeviceStep:
         b.C, b.Th, b.Tw, b.interp = C, T, T, a.interp
         b.grad_texture = self.grad_tex.data_ptr()
         b.tile_any = self.tile_any.data_ptr()
-        self.accum = torch.empty(int(L.lp_backward_workspace_bytes(C, T, T)), dtype=torch.uint8, device=device)
-        if self.accum.numel() and os.environ.get("LP_BWD_VEC", "1") == "1":
+        if accum is not None:
+            # N > 1, fused exchange: the accumulation buffer lives in symmetric memory next to the planar gradient;
+            # the backward leaves the gradient interleaved and lp_allreduce_unpack reduces + unpacks + broadcasts it
+            self.accum = accum.view(torch.uint8)
+            b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
+            b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE | _lib.LP_FLAG_GRAD_INTERLEAVED
+        else:
+            self.accum = torch.empty(int(L.lp_backward_workspace_bytes(C, T, T)), dtype=torch.uint8, device=device)
+        if accum is not None:
+            pass
+        elif self.accum.numel() and os.environ.get("LP_BWD_VEC", "1") == "1":
             b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
             b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
         else:
@@ -331,31 +340,48 @@ def main():
     else:
         auto_allreduce = False
     if world > 1 and args.allreduce != "nccl":
-        try:
-            from latent_nerf_test_b200.parallel import SymmetricGradientBuffer
-            for s in range(args.sets):
-                sb = SymmetricGradientBuffer(C * T * T, device)
-                if args.allreduce == "p2p":
-                    sb.mode = "p2p"
-                elif args.allreduce == "multimem" and sb.mode != "multimem":
-                    raise RuntimeError("no multicast support on this box" + (" (auto: using NCCL)" if auto_allreduce else ""))
-                symm_bufs.append(sb)
-            # self-check against NCCL once: same sum within fp32 tolerance
-            probe = torch.randn(C * T * T, device=device, generator=torch.Generator(device=device).manual_seed(rank))
-            symm_bufs[0].flat[:probe.numel()].copy_(probe)
-            symm_bufs[0].all_reduce()
-            dist.all_reduce(probe)
-            torch.cuda.synchronize(device)
-            if not torch.allclose(symm_bufs[0].flat[:probe.numel()], probe, rtol=1e-5, atol=1e-5):
-                raise RuntimeError("symmetric-memory all-reduce disagrees with NCCL")
-            allreduce_mode = symm_bufs[0].mode
-        except Exception as exc:
-            print(f"bench.py: falling back to NCCL all-reduce ({exc})", file=sys.stderr)
+        from latent_nerf_test_b200.parallel import SymmetricGradientBuffer
+        want_fused = C <= 4 and os.environ.get("LP_EXCHANGE_FUSED", "1") == "1"
+        # attempts, best first: exchange fused with the unpack, then unpack + all-reduce of the planar gradient over
+        # symmetric memory, then NCCL.  Each is self-checked against NCCL once and the verdict is agreed on by all ranks.
+        for fused in ([True, False] if want_fused else [False]):
+            err = None
+            try:
+                symm_bufs = []
+                for s in range(args.sets):
+                    sb = SymmetricGradientBuffer(C * T * T, device, interleaved_texels=T * T if fused else 0, channels=C)
+                    if args.allreduce == "p2p":
+                        sb.mode = "p2p"
+                    elif args.allreduce == "multimem" and sb.mode != "multimem":
+                        raise RuntimeError("no multicast support on this box")
+                    symm_bufs.append(sb)
+                gen = torch.Generator(device=device).manual_seed(rank)
+                if symm_bufs[0].fused:
+                    tex4 = torch.randn(T * T, 4, device=device, generator=gen)         # interleaved accumulation buffer
+                    symm_bufs[0].accum.view(T * T, 4).copy_(tex4)
+                    probe = tex4[:, :C].t().contiguous().reshape(-1)                   # its planar (C, T*T) form
+                else:
+                    probe = torch.randn(C * T * T, device=device, generator=gen)
+                    symm_bufs[0].flat[:probe.numel()].copy_(probe)
+                symm_bufs[0].all_reduce()
+                dist.all_reduce(probe)
+                torch.cuda.synchronize(device)
+                if not torch.allclose(symm_bufs[0].flat[:probe.numel()], probe, rtol=1e-5, atol=1e-5):
+                    raise RuntimeError("symmetric-memory all-reduce disagrees with NCCL")
+            except Exception as exc:
+                err = exc
+            ok = torch.tensor([0 if err else 1], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()):
+                allreduce_mode = symm_bufs[0].mode + (" fused with the unpack" if symm_bufs[0].fused else "")
+                break
+            print(f"bench.py: {'fused ' if fused else ''}symmetric-memory exchange unavailable ({err}); trying the next form", file=sys.stderr)
             symm_bufs, allreduce_mode = [], "nccl"
     for s in range(args.sets):
         radius, theta, phi = make_views(B, 1000 * rank + s)
         gt = symm_bufs[s].view((C, T, T)) if symm_bufs else None
-        sets.append(DeviceStep(geom, w, cameras_for(radius, theta, phi, w["dy"]), 10 * s + 1, device, grad_tex=gt))
+        acc = symm_bufs[s].accum if symm_bufs and symm_bufs[s].fused else None
+        sets.append(DeviceStep(geom, w, cameras_for(radius, theta, phi, w["dy"]), 10 * s + 1, device, grad_tex=gt, accum=acc))
     set_bytes = sum(t.numel() * t.element_size() for t in (sets[0].tex, sets[0].grad_image, sets[0].image, sets[0].mask,
                                                            sets[0].uv, sets[0].grad_tex))
 

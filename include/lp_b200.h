@@ -62,9 +62,12 @@ enum {
                                            dibr_rasterization's valid_faces as the reference calls it with abs() */
     LP_FLAG_SHADE_FEATURES   = 1u << 4, /* interpolate face_features instead of sampling a texture
                                            (Renderer.render_single_view, latent_paint render.py:34-47) */
-    LP_FLAG_GRAD_OVERWRITE   = 1u << 5  /* lp_render_backward with a workspace: grad_texture is written, not
+    LP_FLAG_GRAD_OVERWRITE   = 1u << 5, /* lp_render_backward with a workspace: grad_texture is written, not
                                            accumulated into, so the caller need not zero it */
-    /* bits 24-30 are profiling switches of bench.py (stop-after-stage ablations), not part of the contract */
+    LP_FLAG_GRAD_INTERLEAVED = 1u << 6  /* lp_render_backward with a workspace: leave the gradient in the workspace as
+                                           (Th,Tw,4) texel-interleaved float4 and do not touch grad_texture —
+                                           lp_allreduce_unpack sums it over the ranks and writes the planar gradient */
+    /* bits 20-30 are profiling switches of bench.py (stop-after-stage ablations), not part of the contract */
 };
 
 typedef struct LpForwardArgs {
@@ -202,6 +205,16 @@ int lp_render_step_host(const LpForwardArgs *fwd, const LpBackwardArgs *bwd,
  *                          `world` buffer pointers) — fallback when the box has no multicast support */
 int lp_allreduce_multimem(void *multicast_ptr, int64_t count, int32_t rank, int32_t world, void *stream);
 int lp_allreduce_p2p(void *const *buffer_ptrs_dev, int64_t count, int32_t rank, int32_t world, int32_t phase, void *stream);
+
+/* Exchange fused with the unpack of the vector-RED backward: every rank holds one symmetric allocation with the
+ * texel-interleaved accumulation buffer (ntex float4, what lp_render_backward leaves with LP_FLAG_GRAD_INTERLEAVED)
+ * at byte offset accum_offset and the planar (C,ntex) gradient at byte offset grad_offset.  Rank r sums slice r of
+ * the accumulation buffers of all ranks (multicast_base != NULL: multimem.ld_reduce inside the NVSwitch; else peer
+ * loads in rank order), transposes it to planar in registers and writes it into the gradient of EVERY rank
+ * (multimem.st / peer stores): one kernel instead of unpack + reduce-scatter + all-gather, and every rank ends with
+ * bit-identical sums.  ntex must be a multiple of 4 * world.  Barriers before and after are the caller's, as above. */
+int lp_allreduce_unpack(void *multicast_base, void *const *buffer_ptrs_dev, uint64_t accum_offset, uint64_t grad_offset,
+                        int64_t ntex, int32_t C, int32_t rank, int32_t world, void *stream);
 
 /* Instrumentation (bench.py's roofline leg): while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  lp_timing_collect waits for them, sums the elapsed

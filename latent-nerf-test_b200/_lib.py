@@ -29,10 +29,11 @@ LP_FLAG_REJECT_BEHIND = 1 << 2
 LP_FLAG_CULL_NZ_ZERO = 1 << 3
 LP_FLAG_SHADE_FEATURES = 1 << 4
 LP_FLAG_GRAD_OVERWRITE = 1 << 5
+LP_FLAG_GRAD_INTERLEAVED = 1 << 6
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_render_step_host_async"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_render_step_host_async"]
 
 
 class LpForwardArgs(Structure):
@@ -123,6 +124,8 @@ def lib() -> ctypes.CDLL:
     L.lp_allreduce_multimem.argtypes = [c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p]
     L.lp_allreduce_p2p.restype = c_int32
     L.lp_allreduce_p2p.argtypes = [c_void_p, ctypes.c_int64, c_int32, c_int32, c_int32, c_void_p]
+    L.lp_allreduce_unpack.restype = c_int32
+    L.lp_allreduce_unpack.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, ctypes.c_int64, c_int32, c_int32, c_int32, c_void_p]
     L.lp_render_backward.restype = c_int32
     L.lp_render_backward.argtypes = [POINTER(LpBackwardArgs), c_void_p]
     L.lp_texture_map_forward.restype = c_int32

@@ -75,7 +75,7 @@ class SymmetricGradientBuffer:
     rank owns an equally sized, 16-byte aligned slice.
     """
 
-    def __init__(self, numel: int, device, group=None):
+    def __init__(self, numel: int, device, group=None, interleaved_texels: int = 0, channels: int = 0):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
@@ -87,11 +87,23 @@ class SymmetricGradientBuffer:
         quantum = 4 * self.world
         self.numel = numel
         self.padded = (numel + quantum - 1) // quantum * quantum
-        self.flat = symm.empty(self.padded, dtype=torch.float32, device=device)
-        self.flat.zero_()
-        self.handle = symm.rendezvous(self.flat, self.group.group_name)
+        # fused form (``interleaved_texels`` = Th * Tw of ONE texture with ``channels`` <= 4 planes, numel =
+        # channels * texels): the same allocation also holds the (Th,Tw,4) accumulation buffer the vector-RED
+        # backward scatters into (LP_FLAG_GRAD_INTERLEAVED); lp_allreduce_unpack then reduces, unpacks and
+        # broadcasts in one kernel
+        self.texels, self.channels = int(interleaved_texels), int(channels)
+        self.fused = bool(self.texels) and self.texels % quantum == 0 and 0 < self.channels <= 4 \
+            and numel == self.channels * self.texels
+        self.accum_floats = 4 * self.texels if self.fused else 0
+        self.flat_all = symm.empty(self.padded + self.accum_floats, dtype=torch.float32, device=device)
+        self.flat_all.zero_()
+        self.flat = self.flat_all[:self.padded]
+        self.accum = self.flat_all[self.padded:] if self.fused else None      # (texels, 4) interleaved
+        self.accum_offset = 4 * self.padded                                   # bytes from the allocation's base
+        self.handle = symm.rendezvous(self.flat_all, self.group.group_name)
         self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         self.mode = "multimem" if self.multicast_ptr else "p2p"
+        self.use_fused = self.fused          # callers may switch back to unpack + all-reduce on the planar gradient
 
     def view(self, shape):
         n = 1
@@ -104,7 +116,11 @@ class SymmetricGradientBuffer:
         L, c = self._lib.lib(), self._ctypes
         stream = c.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
         self.handle.barrier(channel=0)                       # every rank's backward has finished
-        if self.mode == "multimem":
+        if self.fused and self.use_fused:
+            mc = c.c_void_p(self.multicast_ptr) if self.mode == "multimem" else None
+            self._lib.check(L.lp_allreduce_unpack(mc, c.c_void_p(self.handle.buffer_ptrs_dev), self.accum_offset, 0,
+                                                  self.texels, self.channels, self.rank, self.world, stream))
+        elif self.mode == "multimem":
             self._lib.check(L.lp_allreduce_multimem(c.c_void_p(self.multicast_ptr), self.padded, self.rank, self.world, stream))
         else:
             ptrs = c.c_void_p(self.handle.buffer_ptrs_dev)

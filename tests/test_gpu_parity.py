@@ -455,3 +455,39 @@ def test_random_scenes_visibility_bit_exact():
             assert_close(image, oi, f"image {it}")
         checked += int((ref.last["face_idx"] >= 0).sum())
     assert checked > 10000
+
+
+def test_allreduce_unpack_single_rank_is_the_unpack():
+    """lp_allreduce_unpack with world = 1 over plain peer pointers: the planar gradient must equal the
+    texel-interleaved accumulation buffer transposed (the exchange kernel's unpack half), and a backward with
+    LP_FLAG_GRAD_INTERLEAVED followed by it must equal the ordinary backward."""
+    from bench import DeviceStep, WORKLOADS, cameras_for, make_views
+    L = _lib.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for C, T in ((3, 64), (4, 32), (1, 16)):
+        ntex = T * T
+        buf = torch.zeros(C * ntex + 4 * ntex, device=DEV)                 # planar gradient, then the accumulation buffer
+        acc = torch.randn(ntex, 4, device=DEV, generator=torch.Generator(device=DEV).manual_seed(C))
+        buf[C * ntex:].copy_(acc.reshape(-1))
+        ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
+        _lib.check(L.lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
+        torch.cuda.synchronize()
+        assert torch.equal(buf[:C * ntex].view(C, ntex), acc[:, :C].t().contiguous())
+    assert L.lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 0, 0, 6, 3, 0, 1, stream) == _lib.LP_ERR_BAD_ARG
+
+    w = dict(WORKLOADS["c2"], B=2, H=96, W=96, T=128)
+    verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
+    geom = (verts.to(DEV).float().contiguous(), faces.to(DEV, torch.int32).contiguous(), uv.to(DEV).float().reshape(-1, 3, 2).contiguous())
+    radius, theta, phi = make_views(w["B"], 9)
+    cams = cameras_for(radius, theta, phi, w["dy"])
+    ref = DeviceStep(geom, w, cams, 1, torch.device(DEV))
+    ntex, C = w["T"] ** 2, w["C"]
+    both = torch.zeros(C * ntex + 4 * ntex, device=DEV)
+    fused = DeviceStep(geom, w, cams, 1, torch.device(DEV), grad_tex=both[:C * ntex].view(C, w["T"], w["T"]), accum=both[C * ntex:])
+    with torch.cuda.stream(torch.cuda.current_stream()):
+        ref.run(); fused.run()
+    ptrs = torch.tensor([both.data_ptr()], dtype=torch.int64, device=DEV)
+    _lib.check(L.lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
+    torch.cuda.synchronize()
+    assert float(ref.grad_tex.abs().sum()) > 0
+    assert_close(fused.grad_tex, ref.grad_tex, "gradient through the fused exchange path", rtol=1e-5, atol=1e-6)

@@ -23,6 +23,23 @@ modes = ["multimem", "p2p"] if sb.multicast_ptr else ["p2p"]
 for m in modes:
     sb.mode = m
     res[m] = timed(sb.all_reduce)
+# the exchange fused with the unpack (3 channels over 1024^2 texels: 16.8 MB interleaved in, 12.6 MB planar out)
+try:
+    T = 1024
+    fb = SymmetricGradientBuffer(3 * T * T, dev, interleaved_texels=T * T, channels=3)
+    for m in (["multimem", "p2p"] if fb.multicast_ptr else ["p2p"]):
+        fb.mode = m
+        res["fused_unpack_" + m] = timed(fb.all_reduce)
+    fb.mode = "multimem" if fb.multicast_ptr else "p2p"
+    gf = torch.cuda.CUDAGraph()
+    sf = torch.cuda.Stream()
+    with torch.cuda.stream(sf):
+        fb.all_reduce(); torch.cuda.synchronize()
+        with torch.cuda.graph(gf, stream=sf):
+            for _ in range(10): fb.all_reduce()
+        res["fused_unpack_" + fb.mode + "_graph"] = timed(gf.replay, 50) / 10
+except Exception as e:
+    res["fused_error"] = str(e)[:200]
 g = torch.cuda.CUDAGraph()
 try:
     sb.mode = modes[0]
