@@ -131,19 +131,25 @@ def import_mesh(path, with_normals=False, with_materials=False):
     return meshio.load_obj(path)
 
 
+def import_off_mesh(path):
+    """``kal.io.off.import_mesh`` (reference mesh.py:16-17)."""
+    return meshio.load_off(path)
+
+
 def make_module() -> types.ModuleType:
     kal = types.ModuleType("kaolin")
     render, cam, mesh = types.ModuleType("kaolin.render"), types.ModuleType("kaolin.render.camera"), \
         types.ModuleType("kaolin.render.mesh")
     ops, ops_mesh = types.ModuleType("kaolin.ops"), types.ModuleType("kaolin.ops.mesh")
-    io, io_obj = types.ModuleType("kaolin.io"), types.ModuleType("kaolin.io.obj")
+    io, io_obj, io_off = types.ModuleType("kaolin.io"), types.ModuleType("kaolin.io.obj"), types.ModuleType("kaolin.io.off")
     cam.generate_perspective_projection = generate_perspective_projection
     cam.generate_transformation_matrix = generate_transformation_matrix
     mesh.prepare_vertices, mesh.rasterize, mesh.dibr_rasterization = prepare_vertices, rasterize, dibr_rasterization
     mesh.texture_mapping, mesh.spherical_harmonic_lighting = texture_mapping, spherical_harmonic_lighting
     ops_mesh.index_vertices_by_faces, ops_mesh.uniform_laplacian = index_vertices_by_faces, uniform_laplacian
     io_obj.import_mesh = import_mesh
-    render.camera, render.mesh, ops.mesh, io.obj = cam, mesh, ops_mesh, io_obj
+    io_off.import_mesh = import_off_mesh
+    render.camera, render.mesh, ops.mesh, io.obj, io.off = cam, mesh, ops_mesh, io_obj, io_off
     kal.render, kal.ops, kal.io = render, ops, io
     kal.__lp_b200__ = True
     return kal
@@ -157,6 +163,6 @@ def install() -> types.ModuleType:
     kal = make_module()
     for name, mod in (("kaolin", kal), ("kaolin.render", kal.render), ("kaolin.render.camera", kal.render.camera),
                       ("kaolin.render.mesh", kal.render.mesh), ("kaolin.ops", kal.ops), ("kaolin.ops.mesh", kal.ops.mesh),
-                      ("kaolin.io", kal.io), ("kaolin.io.obj", kal.io.obj)):
+                      ("kaolin.io", kal.io), ("kaolin.io.obj", kal.io.obj), ("kaolin.io.off", kal.io.off)):
         sys.modules[name] = mod
     return kal

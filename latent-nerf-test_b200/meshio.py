@@ -62,6 +62,30 @@ def load_obj(path: str) -> MeshData:
     return MeshData(v, f, vt, ft)
 
 
+def load_off(path: str) -> MeshData:
+    """Object File Format reader (``kal.io.off.import_mesh``, reference mesh.py:16-17): ``OFF`` header,
+    ``nv nf ne`` counts, vertex rows, then ``3 i j k`` face rows (0-based).  OFF carries no UVs."""
+    with open(path, "r") as fh:
+        tok = [t for line in fh for t in line.split("#", 1)[0].split()]
+    if not tok or not tok[0].upper().startswith("OFF"):
+        raise ValueError(f"{path}: not an OFF file")
+    head = tok[0][3:]                      # "OFF3 4 0" style headers glue the first count to the tag
+    rest = ([head] if head else []) + tok[1:]
+    nv, nf = int(rest[0]), int(rest[1])
+    pos = 3
+    verts = np.asarray(rest[pos:pos + 3 * nv], dtype=np.float32).reshape(nv, 3)
+    pos += 3 * nv
+    faces = []
+    for _ in range(nf):
+        n = int(rest[pos])
+        if n != 3:
+            raise ValueError(f"{path}: only triangular faces are supported, got {n} corners")
+        faces.append([int(rest[pos + 1]), int(rest[pos + 2]), int(rest[pos + 3])])
+        pos += 1 + n
+    f = torch.tensor(np.asarray(faces, dtype=np.int64).reshape(-1, 3))
+    return MeshData(torch.tensor(verts), f, torch.zeros((0, 2)), torch.full((f.shape[0], 3), -1, dtype=torch.int64))
+
+
 def save_npz(mesh: MeshData, path: str) -> None:
     np.savez_compressed(path, vertices=mesh.vertices.numpy(), faces=mesh.faces.numpy().astype(np.int32),
                         uvs=mesh.uvs.numpy(), face_uvs_idx=mesh.face_uvs_idx.numpy().astype(np.int32))
@@ -129,6 +153,68 @@ def face_uv_attributes(mesh: MeshData) -> torch.Tensor:
     if vt is None or ft is None or vt.shape[0] == 0 or ft.numel() == 0 or int(ft.min()) < 0:
         vt, ft = grid_atlas_uvs(mesh.faces.shape[0])
     return vt[ft.reshape(-1)].reshape(1, -1, 3, 2).contiguous()
+
+
+def provision_uvs(mesh, cache_dir=None, save_cache: bool = True):
+    """UV source selection of ``TexturedMeshModel.init_texture_map`` (reference
+    ``src/latent_paint/models/textured_mesh.py:81-109``, same in ``latent_paint_mesh``), returning ``(vt (Nt,2) f32,
+    ft (F,3))``:
+
+    1. the mesh's own UVs when every face has them (``vt.shape[0] > 0 and ft.min() > -1``, :84-87);
+    2. else the cache ``<cache_dir>/vt.pth`` + ``ft.pth`` when both exist (:88-90) — the reference's on-disk format:
+       ``torch.save`` of a CPU float32 ``(Nt,2)`` tensor and a CPU int32 ``(F,3)`` tensor (:103-107);
+    3. else a fresh parametrisation, written to the cache in that format.  The reference runs xatlas here
+       (:91-102); xatlas is not available, so this is the deterministic per-face grid atlas.
+
+    ``mesh`` is a ``MeshData`` or anything with ``vt``/``ft`` (the reference ``Mesh``) or ``uvs``/``face_uvs_idx``."""
+    vt = getattr(mesh, "vt", None) if hasattr(mesh, "vt") else getattr(mesh, "uvs", None)
+    ft = getattr(mesh, "ft", None) if hasattr(mesh, "ft") else getattr(mesh, "face_uvs_idx", None)
+    if vt is not None and ft is not None and vt.shape[0] > 0 and ft.numel() > 0 and int(ft.min()) > -1:
+        return vt, ft
+    vt_cache = os.path.join(str(cache_dir), "vt.pth") if cache_dir is not None else None
+    ft_cache = os.path.join(str(cache_dir), "ft.pth") if cache_dir is not None else None
+    if vt_cache and os.path.isfile(vt_cache) and os.path.isfile(ft_cache):
+        return torch.load(vt_cache), torch.load(ft_cache)
+    vt, ft = grid_atlas_uvs(int(mesh.faces.shape[0]))
+    ft = ft.int()
+    if vt_cache and save_cache:
+        os.makedirs(str(cache_dir), exist_ok=True)
+        torch.save(vt.cpu(), vt_cache)
+        torch.save(ft.cpu(), ft_cache)
+    return vt, ft
+
+
+class Mesh:
+    """Mirror of the reference ``Mesh`` (``src/latent_paint/models/mesh.py:6-48``): ``.vertices``, ``.faces`` on
+    ``device``, ``.vt`` / ``.ft`` as loaded (``ft`` is -1 where a face has no UVs), ``standardize_mesh`` and
+    ``normalize_mesh`` with the reference's arithmetic.  Reads ``.obj`` and ``.off`` without kaolin."""
+
+    def __init__(self, obj_path, device):
+        path = str(obj_path)
+        if ".obj" in path:
+            mesh = load_obj(path)
+        elif ".off" in path:
+            mesh = load_off(path)
+        else:
+            raise ValueError(f"{obj_path} extension not implemented in mesh reader.")
+        self.vertices = mesh.vertices.to(device)
+        self.faces = mesh.faces.to(device)
+        self.ft = mesh.face_uvs_idx
+        self.vt = mesh.uvs
+
+    def standardize_mesh(self, inplace=False):
+        import copy
+        mesh = self if inplace else copy.deepcopy(self)
+        verts = mesh.vertices
+        verts = verts - verts.mean(dim=0)
+        mesh.vertices = verts / torch.std(torch.norm(verts, p=2, dim=1))
+        return mesh
+
+    def normalize_mesh(self, inplace=False, target_scale=1, dy=0):
+        import copy
+        mesh = self if inplace else copy.deepcopy(self)
+        mesh.vertices = normalize_vertices(mesh.vertices, target_scale, dy)
+        return mesh
 
 
 def subdivide(mesh: MeshData, levels: int, project_to_sphere: bool = True) -> MeshData:

@@ -99,6 +99,43 @@ def test_obj_reader_and_packed_meshes(tmp_path):
     assert abs(float(c.norm(dim=1).max()) - 0.6) < 1e-6 and float(c.mean(0).abs().max()) < 1e-6
 
 
+def test_off_reader_mesh_mirror_and_uv_provisioning(tmp_path):
+    """The formats either side of the path (SURVEY.md §8 f rank 2): OFF reader, the reference-shaped Mesh class,
+    and the UV source selection of init_texture_map with its vt.pth / ft.pth cache format."""
+    off = tmp_path / "t.off"
+    off.write_text("OFF\n# comment\n4 2 0\n0 0 0\n1 0 0\n0 1 0\n0 0 2\n3 0 1 2\n3 0 2 3\n")
+    m = meshio.load_off(str(off))
+    assert m.vertices.shape == (4, 3) and m.faces.tolist() == [[0, 1, 2], [0, 2, 3]] and int(m.face_uvs_idx.max()) == -1
+    mesh = meshio.Mesh(str(off), "cpu")
+    assert mesh.vt.shape[0] == 0 and mesh.ft.min() == -1
+    n = mesh.normalize_mesh(target_scale=0.6, dy=0.25)
+    assert mesh.vertices is not n.vertices and abs(float((n.vertices - torch.tensor([0.0, 0.25, 0.0])).norm(dim=1).max()) - 0.6) < 1e-6
+    st = mesh.standardize_mesh()
+    assert abs(float(torch.std(torch.norm(st.vertices, dim=1))) - 1.0) < 1e-5
+    with pytest.raises(ValueError, match="not implemented"):
+        meshio.Mesh("x.ply", "cpu")
+
+    # 1. complete UVs on the mesh win
+    obj = tmp_path / "u.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nf 1/1 2/2 3/3\n")
+    mu = meshio.Mesh(str(obj), "cpu")
+    vt, ft = meshio.provision_uvs(mu, cache_dir=tmp_path / "exp")
+    assert vt is mu.vt and ft is mu.ft and not (tmp_path / "exp").exists()
+    # 3. no UVs, no cache: atlas, written in the reference's cache format (float32 vt, int32 ft, CPU tensors)
+    vt, ft = meshio.provision_uvs(mesh, cache_dir=tmp_path / "exp")
+    assert vt.shape == (6, 2) and ft.shape == (2, 3) and ft.dtype == torch.int32
+    cv, cf = torch.load(tmp_path / "exp" / "vt.pth"), torch.load(tmp_path / "exp" / "ft.pth")
+    assert cv.dtype == torch.float32 and cf.dtype == torch.int32 and torch.equal(cv, vt) and torch.equal(cf, ft)
+    # 2. the cache wins over a new parametrisation (here: a cache someone else wrote, e.g. the reference's xatlas run)
+    torch.save(torch.full((6, 2), 0.5), tmp_path / "exp" / "vt.pth")
+    vt2, ft2 = meshio.provision_uvs(mesh, cache_dir=tmp_path / "exp")
+    assert float(vt2.min()) == 0.5 and torch.equal(ft2, ft)
+    # the kaolin-namespaced readers
+    from latent_nerf_test_b200 import kaolin_compat
+    kal = kaolin_compat.make_module()
+    assert kal.io.off.import_mesh(str(off)).faces.shape == (2, 3) and kal.io.obj.import_mesh(str(obj)).uvs.shape == (3, 2)
+
+
 def test_grid_atlas_and_subdivision():
     vt, ft = meshio.grid_atlas_uvs(7500)
     assert vt.shape == (22500, 2) and ft.shape == (7500, 3)
