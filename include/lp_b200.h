@@ -119,6 +119,13 @@ typedef struct LpForwardArgs {
     /* scratch */
     void          *workspace;
     uint64_t       workspace_bytes;
+    /* model-level composition fused into the face-feature shading (LP_FLAG_SHADE_FEATURES only; all three or none):
+       composed = image * (1 - under_mask) + under_image * under_mask, the reference's
+       pred_back * (1 - mask) + pred_features * mask (src/latent_paint/models/textured_mesh.py:211-212) with this
+       call rendering pred_back (the env sphere) over an earlier texture render (under_image, under_mask) */
+    const float   *under_image;    /* (B,D,H,W) */
+    const float   *under_mask;     /* (B,1,H,W) */
+    float         *composed;       /* out (B,D,H,W) */
 } LpForwardArgs;
 
 typedef struct LpBackwardArgs {
@@ -142,6 +149,8 @@ typedef struct LpBackwardArgs {
        a third of the atomic operations of the planar path */
     void          *workspace;
     uint64_t       workspace_bytes;
+    const float   *under_mask;     /* optional (B,1,H,W), face-feature path: grad_image is dL/d composed and is scaled
+                                      by (1 - under_mask) per pixel (the backward of the fused composition) */
 } LpBackwardArgs;
 
 /* kal.render.mesh.texture_mapping forward (latent_paint render.py:64, latent_paint_mesh render.py:243):
@@ -205,6 +214,25 @@ int lp_render_step_host(const LpForwardArgs *fwd, const LpBackwardArgs *bwd,
  *                          `world` buffer pointers) — fallback when the box has no multicast support */
 int lp_allreduce_multimem(void *multicast_ptr, int64_t count, int32_t rank, int32_t world, void *stream);
 int lp_allreduce_p2p(void *const *buffer_ptrs_dev, int64_t count, int32_t rank, int32_t world, int32_t phase, void *stream);
+
+/* The step after the backward (SURVEY.md §8 f rank 4): torch.optim.Adam on the texture — the reference's optimiser,
+ * Adam(lr, betas=(0.9, 0.99), eps=1e-15), src/latent_paint/training/trainer.py:93-95 — as ONE kernel, optionally
+ * fused with the unpack of the vector-RED backward.  The gradient comes either planar (`grad`, (C,ntex)) or
+ * texel-interleaved (`accum`, (ntex,4) float4, what lp_render_backward leaves with LP_FLAG_GRAD_INTERLEAVED; then
+ * C <= 4 and, if `grad` is non-NULL, the planar gradient is written there as well).  param / exp_avg / exp_avg_sq
+ * are planar (C,ntex) and updated in place with torch's single-tensor Adam arithmetic (no weight decay, no
+ * amsgrad): m += (g - m)(1 - b1); v = v b2 + (1 - b2) g g; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+ * `step` is the 1-based step count AFTER this update. */
+typedef struct LpAdamArgs {
+    const void  *accum;            /* (ntex,4) float4 or NULL */
+    float       *grad;             /* (C,ntex): input when accum is NULL, optional output otherwise */
+    float       *param, *exp_avg, *exp_avg_sq;   /* (C,ntex) */
+    int64_t      ntex;
+    int32_t      C;
+    float        lr, beta1, beta2, eps;
+    int32_t      step;
+} LpAdamArgs;
+int lp_adam_step(const LpAdamArgs *args, void *stream);
 
 /* Exchange fused with the unpack of the vector-RED backward: every rank holds one symmetric allocation with the
  * texel-interleaved accumulation buffer (ntex float4, what lp_render_backward leaves with LP_FLAG_GRAD_INTERLEAVED)

@@ -10,8 +10,8 @@ renderer interface:
 (see INTEGRATION.md).  The directory name carries a hyphen, so the importable alias
 ``latent_nerf_test_b200`` is provided by ``latent_nerf_test_b200.py`` at the repo root.
 """
-from . import _lib, camera, functional, kaolin_compat, meshio  # noqa: F401
+from . import _lib, camera, functional, kaolin_compat, meshio, optim, textured_mesh  # noqa: F401
 from .render import Renderer as LatentPaintRenderer  # noqa: F401
 from .render_mesh import Renderer as LatentPaintMeshRenderer  # noqa: F401
 
-__all__ = ["LatentPaintRenderer", "LatentPaintMeshRenderer", "camera", "functional", "kaolin_compat", "meshio", "_lib"]
+__all__ = ["LatentPaintRenderer", "LatentPaintMeshRenderer", "camera", "functional", "kaolin_compat", "meshio", "optim", "textured_mesh", "_lib"]

@@ -33,7 +33,7 @@ LP_FLAG_GRAD_INTERLEAVED = 1 << 6
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_render_step_host_async"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async"]
 
 
 class LpForwardArgs(Structure):
@@ -50,6 +50,7 @@ class LpForwardArgs(Structure):
         ("image", c_void_p), ("mask", c_void_p), ("uv", c_void_p), ("face_idx", c_void_p), ("bary", c_void_p),
         ("depth", c_void_p), ("normals", c_void_p), ("lighting", c_void_p), ("tile_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
+        ("under_image", c_void_p), ("under_mask", c_void_p), ("composed", c_void_p),
     ]
 
 
@@ -63,6 +64,15 @@ class LpBackwardArgs(Structure):
         ("F", c_int32), ("D", c_int32), ("features_batched", c_int32),
         ("grad_face_features", c_void_p), ("tile_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
+        ("under_mask", c_void_p),
+    ]
+
+
+class LpAdamArgs(Structure):
+    _fields_ = [
+        ("accum", c_void_p), ("grad", c_void_p), ("param", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+        ("ntex", ctypes.c_int64), ("C", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+        ("step", c_int32),
     ]
 
 
@@ -124,6 +134,8 @@ def lib() -> ctypes.CDLL:
     L.lp_allreduce_multimem.argtypes = [c_void_p, ctypes.c_int64, c_int32, c_int32, c_void_p]
     L.lp_allreduce_p2p.restype = c_int32
     L.lp_allreduce_p2p.argtypes = [c_void_p, ctypes.c_int64, c_int32, c_int32, c_int32, c_void_p]
+    L.lp_adam_step.restype = c_int32
+    L.lp_adam_step.argtypes = [POINTER(LpAdamArgs), c_void_p]
     L.lp_allreduce_unpack.restype = c_int32
     L.lp_allreduce_unpack.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, ctypes.c_int64, c_int32, c_int32, c_int32, c_void_p]
     L.lp_render_backward.restype = c_int32

@@ -266,6 +266,100 @@ class _RenderFeatures(torch.autograd.Function):
         return grad_ff, None
 
 
+class _RenderComposed(torch.autograd.Function):
+    """Texture render of the object + face-colour render of the environment sphere + the model-level composition
+    ``pred_back * (1 - mask) + pred_features * mask`` (reference ``src/latent_paint/models/textured_mesh.py:195-212``)
+    as two forward launches chains and no elementwise pass: the composition is written by the shading stage of the
+    second render, and the backward feeds ``dL/d composed`` straight into both scatter kernels (the texture scatter
+    already ignores uncovered pixels, the face-colour scatter scales by ``1 - mask`` per pixel)."""
+
+    @staticmethod
+    def forward(ctx, texture, face_features, tex_cfg: RenderConfig, feat_cfg: RenderConfig):
+        ctx.set_materialize_grads(False)
+        with torch.no_grad():
+            fg, mask, uv, *_ = _RenderTexture.forward(_Scratch(), texture, tex_cfg)
+        tex_ctx = _Scratch.last
+        _require_cuda(face_features, "face_attributes")
+        device = face_features.device
+        ff = face_features.detach().to(torch.float32).contiguous()
+        B, H, W = feat_cfg.B, feat_cfg.H, feat_cfg.W
+        Bf, F, _, D = ff.shape
+        if ff.dim() != 4 or ff.shape[2] != 3 or Bf not in (1, B) or F != feat_cfg.F:
+            raise ValueError(f"face_attributes must have shape (1|B,F,3,D) matching the sphere mesh, got {tuple(ff.shape)}")
+        if tuple(fg.shape) != (B, D, H, W):
+            raise ValueError(f"texture render {tuple(fg.shape)} and face-colour render {(B, D, H, W)} do not match")
+        back = torch.empty((B, D, H, W), dtype=torch.float32, device=device)
+        bmask = torch.empty((B, 1, H, W), dtype=torch.float32, device=device)
+        composed = torch.empty((B, D, H, W), dtype=torch.float32, device=device)
+        face_idx = torch.empty((B, H, W), dtype=torch.int32, device=device)
+        bary = torch.empty((B, H, W, 3), dtype=torch.float32, device=device)
+        a = LpForwardArgs()
+        with torch.cuda.device(device):
+            ws = _fill_common(a, feat_cfg, device)
+            a.flags = feat_cfg.flags | _lib.LP_FLAG_SHADE_FEATURES
+            a.face_features, a.D, a.features_batched = _ptr(ff), D, int(Bf == B and B > 1)
+            a.image, a.mask, a.face_idx, a.bary = _ptr(back), _ptr(bmask), _ptr(face_idx), _ptr(bary)
+            a.under_image, a.under_mask, a.composed = _ptr(fg), _ptr(mask), _ptr(composed)
+            _lib.check(_lib.lib().lp_render_forward(ctypes.byref(a), _stream(device)))
+            launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        ctx.tex_ctx, ctx.feat_cfg = tex_ctx, feat_cfg
+        ctx.ff_shape, ctx.batched = tuple(ff.shape), int(Bf == B and B > 1)
+        ctx.save_for_backward(face_idx, bary, mask, *tex_ctx.saved_tensors)
+        ctx.mark_non_differentiable(mask)
+        return composed, mask, back, fg
+
+    @staticmethod
+    def backward(ctx, g_composed, g_mask, g_back, g_fg):
+        face_idx, bary, mask, uv, tile_any = ctx.saved_tensors
+        device = face_idx.device
+        grad_tex = grad_ff = None
+        # texture: d composed / d foreground = mask, and the texture scatter only sees covered pixels (mask = 1)
+        g_t = g_composed if g_fg is None else (g_fg if g_composed is None else g_composed + g_fg)
+        if g_t is not None and ctx.needs_input_grad[0]:
+            ctx.tex_ctx.saved_tensors = (uv, tile_any)
+            grad_tex, _ = _RenderTexture.backward(ctx.tex_ctx, g_t)
+        if (g_composed is not None or g_back is not None) and ctx.needs_input_grad[1]:
+            cfg = ctx.feat_cfg
+            Bf, F, _, D = ctx.ff_shape
+            b = LpBackwardArgs()
+            if g_back is None:        # the common case: the (1 - mask) factor is applied inside the scatter kernel
+                g = g_composed.to(torch.float32).contiguous()
+                b.under_mask = _ptr(mask)
+            else:
+                g = (g_back if g_composed is None else g_composed * (1 - mask) + g_back).to(torch.float32).contiguous()
+            grad_ff = torch.zeros(ctx.ff_shape, dtype=torch.float32, device=device)
+            b.B, b.H, b.W = face_idx.shape[0], cfg.H, cfg.W
+            b.flags = cfg.flags | _lib.LP_FLAG_SHADE_FEATURES
+            b.grad_image, b.face_idx, b.bary = _ptr(g), _ptr(face_idx), _ptr(bary)
+            b.F, b.D, b.features_batched = F, D, ctx.batched
+            b.grad_face_features = _ptr(grad_ff)
+            with torch.cuda.device(device):
+                _lib.check(_lib.lib().lp_render_backward(ctypes.byref(b), _stream(device)))
+                launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
+        return grad_tex, grad_ff, None, None
+
+
+class _Scratch:
+    """Stand-in for an autograd ctx so ``_RenderTexture.forward`` / ``.backward`` can be reused inside another Function."""
+    last = None
+
+    def __init__(self):
+        _Scratch.last = self
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *tensors):
+        pass
+
+
+def render_composed(texture, face_features, tex_cfg: RenderConfig, feat_cfg: RenderConfig):
+    """→ (composed (B,C,H,W), mask (B,1,H,W), background (B,C,H,W), foreground (B,C,H,W)); gradients flow into
+    ``texture`` and ``face_features``."""
+    return _RenderComposed.apply(texture, face_features, tex_cfg, feat_cfg)
+
+
 def render_texture(texture, cfg: RenderConfig):
     """→ (image (B,C,H,W), mask (B,1,H,W), uv (B,H,W,2), face_idx|None, bary|None, depth|None,
     normals|None, lighting|None)."""

@@ -64,6 +64,18 @@ class Renderer:
             self.last_buffers = {"face_idx": face_idx, "bary": bary, "depth": depth, "camera": cfg.cameras}
         return image, mask
 
+    def render_train_composed(self, verts, faces, uv_face_attr, texture_map, env_sphere, background_sphere_colors,
+                              elev=0, azim=0, radius=2, look_at_height=0.0):
+        """The training-time render of ``TexturedMeshModel.render_train`` (reference
+        ``src/latent_paint/models/textured_mesh.py:195-212``) in one call: ``render_single_view_texture`` of the
+        object, ``render_single_view`` of the environment sphere with the same camera, and
+        ``pred_back * (1 - mask) + pred_features * mask`` fused into the second render.
+        → ``(image, mask, background, foreground)``, gradients into ``texture_map`` and ``background_sphere_colors``."""
+        tex_cfg = self._config(verts, faces, elev, azim, radius, look_at_height, self.dim, False)
+        tex_cfg.face_uv = functional._f32(uv_face_attr, self.device).reshape(-1, 3, 2)
+        feat_cfg = self._config(env_sphere.vertices, env_sphere.faces, elev, azim, radius, look_at_height, self.dim, False)
+        return functional.render_composed(texture_map, background_sphere_colors.to(self.device), tex_cfg, feat_cfg)
+
     def render_single_view_texture(self, verts, faces, uv_face_attr, texture_map, elev=0, azim=0, radius=2,
                                    look_at_height=0.0, dims=None, white_background=False):
         """``(image (1,C,H,W), mask (1,1,H,W))`` of a UV-textured mesh (reference render.py:50-69);

@@ -147,3 +147,29 @@ class LatentPaintMeshRendererRef:
             image = image + 1 * (1 - mask)
         self.last = {"face_idx": face_idx, "uv": uv, "camera": M}
         return image.permute(0, 3, 1, 2), mask.permute(0, 3, 1, 2), normals.permute(0, 3, 1, 2), lighting
+
+
+def render_train_ref(ref: "LatentPaintRendererRef", mesh_vertices, mesh_faces, face_attributes, texture_img,
+                     env_vertices, env_faces, background_sphere_colors, theta, phi, radius, dy=0.25, latent_mode=True):
+    """Mirror of ``TexturedMeshModel.render_train`` (reference ``src/latent_paint/models/textured_mesh.py:187-220``)
+    over a renderer with the reference's ``Renderer`` interface (this module's mirror or the real class run by
+    ``oracle/reference_glue.py``): object render, environment-sphere render, ``mask.detach()``, the composition and
+    the bicubic resize to the 64 x 64 latent grid.  ``env_vertices`` / ``env_faces`` stand for ``self.env_sphere``."""
+    import torch.nn.functional as F
+    pred_features, mask = ref.render_single_view_texture(mesh_vertices, mesh_faces, face_attributes, texture_img,
+                                                         elev=theta, azim=phi, radius=radius, look_at_height=dy)   # :195-202
+    if isinstance(ref, LatentPaintRendererRef):
+        pred_back, _ = ref.render_single_view(env_vertices, env_faces, background_sphere_colors, elev=theta, azim=phi,
+                                              radius=radius, look_at_height=dy)                                  # :204-209
+    else:                                      # the real reference Renderer takes a mesh object (render.py:34)
+        import types
+        pred_back, _ = ref.render_single_view(types.SimpleNamespace(vertices=env_vertices, faces=env_faces),
+                                              background_sphere_colors, elev=theta, azim=phi, radius=radius, look_at_height=dy)
+    mask = mask.detach()                                                                                         # :211
+    pred_map = pred_back * (1 - mask) + pred_features * mask                                                     # :212
+    if latent_mode and mask.shape[-1] != 64:                                                                      # :214-218
+        mask = F.interpolate(mask, (64, 64), mode='bicubic')
+        pred_back = F.interpolate(pred_back, (64, 64), mode='bicubic')
+        pred_features = F.interpolate(pred_features, (64, 64), mode='bicubic')
+        pred_map = F.interpolate(pred_map, (64, 64), mode='bicubic')
+    return {'image': pred_map, 'mask': mask, 'background': pred_back, 'foreground': pred_features}

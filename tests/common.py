@@ -24,6 +24,12 @@ def scene(shape, scale, dy, subdivide=0):
     return verts, m.faces, lp.meshio.face_uv_attributes(m)
 
 
+def scene_raw(shape):
+    """Un-normalised mesh (the environment sphere is used at its own radius-20 scale, reference textured_mesh.py:53-54)."""
+    m = lp.meshio.find_shape(shape)
+    return m.vertices, m.faces, m
+
+
 def rnd(shape, seed, scale=1.0):
     return scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
 

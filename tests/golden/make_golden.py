@@ -104,11 +104,36 @@ def mesh_texture(case, shape, dims, T, C, B, is_body, white, radius_float=None):
          face_idx=kaolin_shim.LAST["face_idx"].to(torch.int32), grad_texture=tex.grad)
 
 
+def latent_paint_render_train(case, dims, elev, azim, radius):
+    """TexturedMeshModel.render_train (reference src/latent_paint/models/textured_mesh.py:187-220): the model class
+    cannot be imported (hard-coded .cuda(), xatlas), so its render lines are restated in
+    oracle/renderer_ref.render_train_ref and run here over the reference's REAL Renderer class."""
+    from oracle import renderer_ref
+    kaolin_shim.RASTER_IMPL = "brute"
+    R = reference_glue.load_latent_paint_renderer()
+    m, env = lp.meshio.find_shape("blub"), lp.meshio.find_shape("env_sphere")
+    verts = lp.meshio.normalize_vertices(m.vertices, 0.6, 0.25)
+    uv = lp.meshio.face_uv_attributes(m)
+    tex = rnd((1, 4, 128, 128), 1, 0.4).requires_grad_(True)
+    colors = torch.rand(1, env.faces.shape[0], 3, 4, generator=torch.Generator().manual_seed(3)).requires_grad_(True)
+    r = R("cpu", dim=dims, interpolation_mode="bilinear")
+    out = renderer_ref.render_train_ref(r, verts, m.faces, uv, tex, env.vertices, env.faces, colors, elev, azim, radius, dy=0.25)
+    g = rnd(tuple(out["image"].shape), 4)
+    out["image"].backward(g)
+    save(case, dims=np.array(dims), elev=elev, azim=azim, radius=radius, texture=tex, colors=colors, grad_image=g,
+         image=out["image"].contiguous(), mask=out["mask"].contiguous(), background=out["background"].contiguous(),
+         foreground=out["foreground"].contiguous(), grad_texture=tex.grad, grad_colors=colors.grad)
+
+
 if __name__ == "__main__":
     assert reference_glue.available(), "needs /root/reference"
+    if len(sys.argv) > 1 and sys.argv[1] == "render_train":      # only the fixture added after the first freeze
+        latent_paint_render_train("lp_render_train_blub", (64, 64), 1.0, 0.7, 1.25)
+        sys.exit(0)
     pack_meshes()
     latent_paint_texture("lp_blub_nearest", "blub", 0.6, 0.25, (64, 64), 128, 4, "nearest", 1.0, 0.7, 1.25, False)
     latent_paint_texture("lp_blub_bilinear_white", "blub", 0.6, 0.25, (96, 96), 128, 3, "bilinear", 0.6, 2.1, 1.1, True)
     latent_paint_colors("lp_env_sphere_colors", (64, 64), 1.0, 0.7, 1.25)
     mesh_texture("mesh_sphere_body_b3", "sphere", (64, 64), 32, 4, 3, True, False)
     mesh_texture("mesh_teddy_head_white", "teddy", (48, 48), 64, 3, 2, False, True, radius_float=2.0)
+    latent_paint_render_train("lp_render_train_blub", (64, 64), 1.0, 0.7, 1.25)

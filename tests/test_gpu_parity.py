@@ -491,3 +491,91 @@ def test_allreduce_unpack_single_rank_is_the_unpack():
     torch.cuda.synchronize()
     assert float(ref.grad_tex.abs().sum()) > 0
     assert_close(fused.grad_tex, ref.grad_tex, "gradient through the fused exchange path", rtol=1e-5, atol=1e-6)
+
+
+def test_fused_render_train_composition():
+    """SURVEY.md §8 f rank 1: object render + environment-sphere render + pred_back * (1 - mask) + pred_features * mask
+    (reference textured_mesh.py:187-220) through the fused composition, against the vectors frozen from the
+    reference's real Renderer class, against the unfused calls on the GPU, and the resize branch against the oracle."""
+    gd = load_golden("lp_render_train_blub")
+    verts, faces, uv = scene("blub", 0.6, 0.25)
+    env = lp.meshio.find_shape("env_sphere")
+    envm = _Mesh(env.vertices.to(DEV), env.faces.to(DEV))
+    objm = _Mesh(verts.to(DEV), faces.to(DEV))
+    view = dict(theta=float(gd["elev"]), phi=float(gd["azim"]), radius=float(gd["radius"]))
+    tex = torch.tensor(gd["texture"], device=DEV).requires_grad_(True)
+    colors = torch.tensor(gd["colors"], device=DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=tuple(int(d) for d in gd["dims"]), interpolation_mode="bilinear")
+    out = lp.textured_mesh.render_train(r, objm, uv.to(DEV), tex, envm, colors, dy=0.25, **view)
+    assert np.array_equal(out["mask"].cpu().numpy(), gd["mask"])
+    for k in ("image", "background", "foreground"):
+        assert_close(out[k], gd[k], k)
+    out["image"].backward(torch.tensor(gd["grad_image"], device=DEV))
+    assert_close(tex.grad, gd["grad_texture"], "grad_texture")
+    assert_close(colors.grad, gd["grad_colors"], "grad_colors")
+
+    # the unfused sequence on the same kernels gives the same bits forward (same expression, same order)
+    fg, mask = r.render_single_view_texture(objm.vertices, objm.faces, uv.to(DEV), tex.detach(), elev=view["theta"],
+                                            azim=view["phi"], radius=view["radius"], look_at_height=0.25)
+    bg, _ = r.render_single_view(envm, colors.detach(), elev=view["theta"], azim=view["phi"], radius=view["radius"], look_at_height=0.25)
+    assert torch.equal(out["foreground"], fg) and torch.equal(out["background"], bg)
+    assert torch.equal(out["image"], bg * (1 - mask) + fg * mask)
+
+    # gradients arriving on the other outputs as well (not the reference's loss, but autograd allows it)
+    tex2 = tex.detach().clone().requires_grad_(True); col2 = colors.detach().clone().requires_grad_(True)
+    o2 = lp.textured_mesh.render_train(r, objm, uv.to(DEV), tex2, envm, col2, dy=0.25, **view)
+    g1, g2, g3 = (rnd((1, 4, 64, 64), s).to(DEV) for s in (11, 12, 13))
+    (o2["image"] * g1 + o2["background"] * g2 + o2["foreground"] * g3).sum().backward()
+    tex3 = tex.detach().clone().requires_grad_(True); col3 = colors.detach().clone().requires_grad_(True)
+    fg3, m3 = r.render_single_view_texture(objm.vertices, objm.faces, uv.to(DEV), tex3, elev=view["theta"], azim=view["phi"],
+                                           radius=view["radius"], look_at_height=0.25)
+    bg3, _ = r.render_single_view(envm, col3, elev=view["theta"], azim=view["phi"], radius=view["radius"], look_at_height=0.25)
+    ((bg3 * (1 - m3) + fg3 * m3) * g1 + bg3 * g2 + fg3 * g3).sum().backward()
+    assert_close(tex2.grad, tex3.grad, "grad_texture, all outputs used")
+    assert_close(col2.grad, col3.grad, "grad_colors, all outputs used")
+
+    # resize branch (render grid != 64 in latent mode): bicubic to 64 x 64, against the CPU oracle
+    r96 = lp.LatentPaintRenderer(DEV, dim=(96, 96), interpolation_mode="bilinear")
+    o96 = lp.textured_mesh.render_train(r96, objm, uv.to(DEV), tex.detach(), envm, colors.detach(), dy=0.25, **view)
+    ref96 = renderer_ref.LatentPaintRendererRef(dim=(96, 96), interpolation_mode="bilinear")
+    e96 = renderer_ref.render_train_ref(ref96, verts, faces, uv, tex.detach().cpu(), env.vertices, env.faces,
+                                        colors.detach().cpu(), view["theta"], view["phi"], view["radius"], dy=0.25)
+    for k in ("image", "mask", "background", "foreground"):
+        assert tuple(o96[k].shape[-2:]) == (64, 64)
+        assert_close(o96[k], e96[k], k + " (resized)", rtol=1e-4, atol=2e-5)
+
+
+def test_fused_adam_matches_torch_adam():
+    """SURVEY.md §8 f rank 4: the reference's optimiser (Adam, betas (0.9, 0.99), eps 1e-15, trainer.py:93-95) as one
+    kernel, against torch.optim.Adam on the CPU (fp32 tolerance), planar gradients and the interleaved accumulation
+    buffer of the vector-RED backward (unpack fused into the update)."""
+    g = torch.Generator().manual_seed(5)
+    for shape in ((1, 4, 32, 32), (1, 3, 17, 19)):            # 17 * 19 texels: the non-vector tail
+        p_ref = torch.nn.Parameter(0.4 * torch.randn(*shape, generator=g))
+        p_gpu = p_ref.detach().clone().to(DEV).requires_grad_(True)
+        p_acc = p_ref.detach().clone().to(DEV)
+        ref = torch.optim.Adam([p_ref], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+        opt = lp.optim.FusedAdam([p_gpu], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+        opt_acc = lp.optim.FusedAdam([p_acc], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+        C, ntex = shape[1], shape[2] * shape[3]
+        for step in range(6):
+            grad = torch.randn(*shape, generator=g) * (10.0 ** (step - 3))
+            p_ref.grad = grad.clone()
+            ref.step()
+            p_gpu.grad = grad.to(DEV)
+            opt.step()
+            accum = torch.zeros(ntex, 4, device=DEV)
+            accum[:, :C] = grad.reshape(C, ntex).t().to(DEV)
+            planar = torch.empty(shape, device=DEV)
+            opt_acc.step_from_accum(p_acc, accum, grad_out=planar)
+            assert torch.equal(planar.cpu(), grad)
+            assert_close(p_gpu, p_ref, f"param after step {step + 1}", rtol=1e-5, atol=1e-6)
+            assert_close(p_acc, p_ref, f"param (from accum) after step {step + 1}", rtol=1e-5, atol=1e-6)
+        st, rst = opt.state[id(p_gpu)], ref.state[p_ref]
+        assert st["step"] == int(rst["step"])
+        assert_close(st["exp_avg"], rst["exp_avg"], "exp_avg", rtol=1e-5, atol=1e-7)
+        assert_close(st["exp_avg_sq"], rst["exp_avg_sq"], "exp_avg_sq", rtol=1e-5, atol=1e-9)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lp.optim.FusedAdam([torch.zeros(4)])
+    a = _lib.LpAdamArgs()
+    assert _lib.lib().lp_adam_step(ctypes.byref(a), None) == _lib.LP_ERR_BAD_ARG

@@ -6,7 +6,7 @@ import torch
 
 from oracle import kaolin_shim as kal
 from oracle import reference_glue, renderer_ref
-from tests.common import assert_close, load_golden, rnd, scene
+from tests.common import assert_close, load_golden, rnd, scene, scene_raw
 
 
 def _random_soup(B, F, seed, behind=False):
@@ -180,3 +180,30 @@ def test_mirror_equals_reference_glue():
         verts, faces, uv, tex, th, ph, rad, dims=(32, 32), is_body=False)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_render_train_mirror_reproduces_golden():
+    """Model-level composition (reference textured_mesh.py:187-220): the travelling mirror over the mirror renderer
+    must reproduce the vectors frozen from the reference's real Renderer class."""
+    gd = load_golden("lp_render_train_blub")
+    verts, faces, uv = scene("blub", 0.6, 0.25)
+    env_v, env_f, _ = scene_raw("env_sphere")
+    tex = torch.tensor(gd["texture"]).requires_grad_(True)
+    colors = torch.tensor(gd["colors"]).requires_grad_(True)
+    ref = renderer_ref.LatentPaintRendererRef(dim=tuple(int(d) for d in gd["dims"]), interpolation_mode="bilinear")
+    out = renderer_ref.render_train_ref(ref, verts, faces, uv, tex, env_v, env_f, colors, float(gd["elev"]),
+                                        float(gd["azim"]), float(gd["radius"]), dy=0.25)
+    out["image"].backward(torch.tensor(gd["grad_image"]))
+    assert np.array_equal(out["mask"].numpy(), gd["mask"])
+    for k in ("image", "background", "foreground"):
+        assert_close(out[k], gd[k], k)
+    assert_close(tex.grad, gd["grad_texture"], "grad_texture")
+    assert_close(colors.grad, gd["grad_colors"], "grad_colors")
+    # the composition really mixes both renders: background where the mask is 0, foreground where it is 1
+    m = torch.tensor(gd["mask"]).bool().expand(1, 4, -1, -1)
+    assert np.array_equal(gd["image"][m.numpy()], gd["foreground"][m.numpy()])
+    assert np.array_equal(gd["image"][~m.numpy()], gd["background"][~m.numpy()])
+    # resize branch: a 96 x 96 render comes back on the 64 x 64 latent grid (bicubic, :214-218)
+    ref96 = renderer_ref.LatentPaintRendererRef(dim=(96, 96), interpolation_mode="bilinear")
+    out96 = renderer_ref.render_train_ref(ref96, verts, faces, uv, tex.detach(), env_v, env_f, colors.detach(), 1.0, 0.7, 1.25)
+    assert all(tuple(out96[k].shape[-2:]) == (64, 64) for k in ("image", "mask", "background", "foreground"))
