@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster", "deep"],
                     help="overlap texture-independent stages of later steps with step k on other streams: 'geometry' = setup + "
                          "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1), 'deep' = three stages on three "
-                         "streams (geometry | visibility/uv | texture fetch + backward + exchange); auto = geometry at N=1, raster at N>1")
+                         "streams (geometry | visibility/uv | texture fetch + backward + exchange); auto = deep")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
                     help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
                          "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
@@ -406,8 +406,8 @@ def main():
     # --pipeline: the texture-independent stages of the next step (geometry, bins, visibility, uv) run on a
     # second stream while the current step fetches the texture, back-propagates (and all-reduces); each
     # buffer set has its own workspace and saved-uv buffer
-    if args.pipeline == "auto":
-        args.pipeline = "geometry" if world == 1 else "raster"
+    if args.pipeline == "auto":       # measured: 82 us/step deep vs 89 geometry vs 102 raster at N = 1; 123 vs 138 vs 124 at N = 2
+        args.pipeline = "deep"
     pipe_deep = args.pipeline == "deep"
     pipe_raster = args.pipeline == "raster" or pipe_deep
     args.pipeline = None if args.pipeline == "off" else args.pipeline
@@ -552,25 +552,36 @@ def main():
         with torch.cuda.stream(stream):
             L.lp_timing_enable(1)
             n_prof = min(args.steps, 200)
-            for i in range(n_prof):
-                sets[i % len(sets)].run()
+            for i in range(n_prof):                 # the kernels of the timed region, one after the other
+                if pipe_raster:
+                    sets[i % len(sets)].prepare(h_main, True)
+                    sets[i % len(sets)].shade_backward(h_main, stream, True)
+                else:
+                    sets[i % len(sets)].run()
             torch.cuda.synchronize(device)
             timings = _lib.collect_timings()
             L.lp_timing_enable(0)
         per_kernel = {k: 1e3 * v[0] / v[1] for k, v in timings.items()}           # µs per launch
         fwd_bytes, bwd_bytes = algorithmic_bytes(V, F, H, W, C, T, B)
+        if pipe_raster:
+            # split forward: the tile kernel writes mask + saved uv only; k_shade reads the uv and the texture and
+            # writes the image (its uv read is extra traffic the fused form does not have, so not counted)
+            shade_bytes = B * H * W * 4 * C + 4 * C * T * T
+            fwd_bytes_tile = fwd_bytes - shade_bytes
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.isfile(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        kb = {"k_raster_shade": fwd_bytes, "k_backward_texture": bwd_bytes}
+        kb = {"k_raster_shade": fwd_bytes_tile if pipe_raster else fwd_bytes, "k_backward_texture": bwd_bytes}
+        if pipe_raster:
+            kb["k_shade"] = shade_bytes
         dom = max(kb, key=lambda k: per_kernel.get(k, 0.0))
         achieved = kb[dom] / (per_kernel[dom] * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")                       # dram bytes per launch from ncu --set full
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get(dom)
+            traffic = json.load(open(tp)).get(dom + ("_split" if pipe_raster and dom == "k_raster_shade" else ""))
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kb[dom], "us_per_launch": per_kernel[dom],
