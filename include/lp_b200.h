@@ -21,6 +21,12 @@
  *                           into the face features: pred.backward(gradient=grad)
  *                                                                    src/latent_paint_mesh/training/trainer.py:656-660
  *   lp_render_step_host     one forward+backward through host buffers (what bench.py's e2e times)
+ *   lp_render_forward with under_image / under_mask / composed
+ *                           pred_back * (1 - mask) + pred_features * mask   src/latent_paint/models/textured_mesh.py:211-212
+ *   lp_allreduce_*          the texture-gradient sum over the ranks (new: the reference is single-GPU)
+ *   lp_adam_step            torch.optim.Adam(lr, betas=(0.9, 0.99), eps=1e-15).step()
+ *                                                                    src/latent_paint/training/trainer.py:93-95
+ *                                                                    src/latent_paint_mesh/training/trainer.py:326-328
  *
  * Conventions: every pointer is caller-owned; device pointers unless the name ends in _host.
  * All floating point is fp32, indices int32.  Calls only enqueue work on the given stream
