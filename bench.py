@@ -309,7 +309,7 @@ def main():
                     help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
                          "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
-    ap.add_argument("--cpu-views", type=int, default=40, help="views timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--cpu-views", type=int, default=160, help="views timed for cpu_baseline, about 10-30 s of CPU work (0 = skip)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.warmup < 3:
