@@ -212,3 +212,57 @@ def test_kaolin_compat_surface_and_install():
         for k in [k for k in sys.modules if k == "kaolin" or k.startswith("kaolin.")]:
             del sys.modules[k]
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+def test_micro_face_sign_pretest_never_rejects_a_covered_pixel():
+    """k_setup_count skips the decree's divisions when `w_k * sign(s) < -|s| * 1e-30` for some k (csrc/lp_b200.cu,
+    micro-face path).  That shortcut must never reject a pixel the exact test `w_k / s >= 0` accepts — including
+    quotients that underflow to -0 (which the decree accepts), zeros, infinities and NaNs.  numpy float32 follows the
+    same IEEE rules as the kernel compiled with -fmad=false."""
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    mag = np.float32(10.0) ** rng.uniform(-44, 38, n).astype(np.float32)
+    w = (mag * rng.choice(np.array([-1.0, 1.0], np.float32), n)).astype(np.float32)
+    s = (np.float32(10.0) ** rng.uniform(-8, 38, n).astype(np.float32) * rng.choice(np.array([-1.0, 1.0], np.float32), n)).astype(np.float32)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-38, -1e-38, 3e38, -3e38, 1e-8, -1e-8], np.float32)
+    w = np.concatenate([w, np.repeat(special, len(special))])
+    s = np.concatenate([s, np.tile(special, len(special))])
+    with np.errstate(all="ignore"):
+        sg = np.copysign(np.float32(1.0), s)
+        guard = (np.abs(s) * np.float32(1e-30)).astype(np.float32)
+        rejected = (w * sg).astype(np.float32) < -guard
+        accepted_exact = (w / s).astype(np.float32) >= 0
+    assert not np.any(rejected & accepted_exact)
+    assert rejected.mean() > 0.3                     # and the shortcut does fire on ordinary negative quotients
+
+
+def test_depth_face_key_order():
+    """The 64-bit key of the micro-face path, `orderable(z0) << 32 | (0xFFFFFFFF - face)`: its maximum must be
+    "largest z0, ties to the lowest face id", and the float <-> uint map must round-trip."""
+    z = np.array([-np.inf, -3e38, -2.5, -1.0, -1e-30, -1e-45, 0.0, 1e-45, 1e-30, 1.0, 7.5, 3e38, np.inf], np.float32)
+    u = z.view(np.uint32)
+    o = np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+    assert np.all(np.diff(o.astype(np.int64)) > 0)                     # strictly increasing with z
+    back = np.where(o & 0x80000000, o ^ 0x80000000, ~o).astype(np.uint32).view(np.float32)
+    assert np.array_equal(back, z)
+    assert o.min() > 0                                                  # key 0 is free to mean "no face"
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        zs = rng.choice(z[1:-1], 6).astype(np.float32)
+        fs = rng.permutation(1000)[:6].astype(np.uint32)
+        us = zs.view(np.uint32)
+        os_ = np.where(us & 0x80000000, ~us, us | 0x80000000).astype(np.uint64)
+        keys = (os_ << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - fs.astype(np.uint64))
+        k = int(np.argmax(keys))
+        best = max(zs)
+        assert zs[k] == best and fs[k] == min(f for zz, f in zip(zs, fs) if zz == best)
+
+
+def test_host_side_errors_of_the_widened_rows():
+    """The rows added per SURVEY.md §8(f) fail loudly on the host before touching a device."""
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lp.optim.FusedAdam([torch.zeros(8)])
+    with pytest.raises(ValueError, match="linear_rgb_estimator"):
+        lp.textured_mesh.render_train(None, None, None, None, None, torch.zeros(1, 4, 3, 4), 1.0, 0.5, 1.25, latent_mode=False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        lp.LatentPaintRenderer("cpu")
