@@ -276,9 +276,9 @@ class _RenderComposed(torch.autograd.Function):
     @staticmethod
     def forward(ctx, texture, face_features, tex_cfg: RenderConfig, feat_cfg: RenderConfig):
         ctx.set_materialize_grads(False)
+        tex_ctx = _Scratch()
         with torch.no_grad():
-            fg, mask, uv, *_ = _RenderTexture.forward(_Scratch(), texture, tex_cfg)
-        tex_ctx = _Scratch.last
+            fg, mask, uv, *_ = _RenderTexture.forward(tex_ctx, texture, tex_cfg)
         _require_cuda(face_features, "face_attributes")
         device = face_features.device
         ff = face_features.detach().to(torch.float32).contiguous()
@@ -341,10 +341,8 @@ class _RenderComposed(torch.autograd.Function):
 
 class _Scratch:
     """Stand-in for an autograd ctx so ``_RenderTexture.forward`` / ``.backward`` can be reused inside another Function."""
-    last = None
 
     def __init__(self):
-        _Scratch.last = self
         self.saved_tensors = ()
 
     def save_for_backward(self, *tensors):
