@@ -266,3 +266,24 @@ def test_host_side_errors_of_the_widened_rows():
         lp.textured_mesh.render_train(None, None, None, None, None, torch.zeros(1, 4, 3, 4), 1.0, 0.5, 1.25, latent_mode=False)
     with pytest.raises(RuntimeError, match="no CPU path"):
         lp.LatentPaintRenderer("cpu")
+
+
+def test_workspace_size_follows_the_micro_face_rule():
+    """lp_workspace_bytes is a pure host function: dense meshes (16 F >= H W) get the 8-byte-per-pixel key buffer of
+    the micro-face path on top of the per-face records, sparse ones do not; bad sizes give 0."""
+    L = _lib.lib()
+    B, H, W = 2, 64, 64
+    sparse, dense = L.lp_workspace_bytes(B, 255, H, W), L.lp_workspace_bytes(B, 256, H, W)      # 16 * 256 == 64 * 64
+    per_face = 3 * 16 + 4 + 2 * 16 + 4 + 4 * 4                                                    # records, cellinfo, edge tests, pairs
+    assert dense - sparse >= 8 * B * H * W and dense - sparse <= 8 * B * H * W + B * per_face + 16 * 256
+    assert sparse >= B * 255 * per_face
+    assert L.lp_workspace_bytes(0, 10, 8, 8) == 0 and L.lp_workspace_bytes(1, 10, 0, 8) == 0
+    assert L.lp_backward_workspace_bytes(3, 1024, 1024) == 16 * 1024 * 1024 and L.lp_backward_workspace_bytes(5, 8, 8) == 0
+
+
+def test_algorithmic_bytes_match_the_survey():
+    """bench.py's roofline numerator is SURVEY.md §8(d)'s formula: config 2 = 119.96 MB per 8-view step."""
+    import bench
+    fwd, bwd = bench.algorithmic_bytes(3750, 7500, 512, 512, 3, 1024, 8)
+    assert fwd + bwd == 8 * (12 * 3750 + 36 * 7500 + 512 * 512 * (8 * 3 + 20)) + 8 * 3 * 1024 * 1024 == 119960512
+    assert abs((fwd + bwd) / 6461.5e9 * 1e6 - 18.57) < 0.01                                      # µs at the measured HBM peak
