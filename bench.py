@@ -4,10 +4,13 @@
 Workload (``config.workload``): BASELINE.json configs[1] — shapes/nascar.obj (V=3750, F=7500,
 deterministic grid-atlas UVs), 3-channel 1024² RGB texture, 512×512 render, batch of
 8 random views per GPU, latent_paint flavour, bilinear.  One *step* = one forward render of the 8
-views + one backward scatter of a dense upstream gradient into the texture gradient (+ one NCCL
-all-reduce of that gradient when N > 1: views shard over ranks, weak scaling).
+views + one backward scatter of a dense upstream gradient into the texture gradient (+ one sum of
+that gradient over the ranks when N > 1 — the library's exchange kernels over symmetric memory, NCCL
+as the fallback: views shard over ranks, weak scaling).
 
-  value      device-timed views/s, inputs resident in HBM, steps replayed from CUDA graphs
+  value      device-timed views/s, inputs resident in HBM, steps replayed from CUDA graphs; by
+             default a three-stream pipeline (geometry | visibility | texture fetch + backward +
+             exchange) overlaps the texture-independent stages of later steps (--pipeline off: serial)
   e2e        same metric through lp_render_step_host with pinned HOST buffers (H2D + D2H inside)
   roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration (an
              instrumented eager pass over the same steps) against MEASURED_PEAKS.json HBM GB/s
