@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py — views/sec of the Latent-Paint render path (forward + backward), BASELINE.json's metric.
 
-Workload (``config.workload``): BASELINE.json configs[1] — shapes/nascar.obj (V=3750, F=7500,
+Default workload (``config.workload``): BASELINE.json configs[1] — shapes/nascar.obj (V=3750, F=7500,
 deterministic grid-atlas UVs), 3-channel 1024² RGB texture, 512×512 render, batch of
-8 random views per GPU, latent_paint flavour, bilinear.  One *step* = one forward render of the 8
+8 random views per GPU, latent_paint flavour, bilinear.  One *step* = one forward render of the
 views + one backward scatter of a dense upstream gradient into the texture gradient (+ one sum of
 that gradient over the ranks when N > 1 — the library's exchange kernels over symmetric memory, NCCL
-as the fallback: views shard over ranks, weak scaling).
+as the fallback: views shard over ranks, weak scaling).  ``--workload c3`` (configs[2]: teddy, 64 views
+in total sharded over the ranks, latent_paint_mesh flavour — strong scaling) and ``--workload c4``
+(configs[3]: 1.31 M-face sphere, 1024², 16 views per GPU) run the same step on the other configs;
+the default run also appends the configs[2] strong-scaling measurement as ``strong_scaling``.
 
-  value      device-timed views/s, inputs resident in HBM, steps replayed from CUDA graphs; by
-             default a three-stream pipeline (geometry | visibility | texture fetch + backward +
-             exchange) overlaps the texture-independent stages of later steps (--pipeline off: serial)
-  e2e        same metric through lp_render_step_host with pinned HOST buffers (H2D + D2H inside)
+  value      device-timed views/s, inputs resident in HBM, steps replayed from CUDA graphs (the graph is
+             uploaded and replayed once during warm-up); by default a three-stream pipeline (geometry |
+             visibility | texture fetch + backward + exchange) overlaps the texture-independent stages
+             of later steps (--pipeline off: serial)
+  e2e        same metric through lp_render_step_host with pinned HOST buffers (H2D + D2H inside), on
+             every rank at once, aggregated
   roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration (an
              instrumented eager pass over the same steps) against MEASURED_PEAKS.json HBM GB/s
   cpu_baseline  the oracle (reference glue mirror over the torch kaolin restatement) on the host cores
@@ -37,26 +42,43 @@ import latent_nerf_test_b200 as lp  # noqa: E402
 from latent_nerf_test_b200 import _lib  # noqa: E402
 
 WORKLOADS = {
-    # name: shape, scale, dy, H, W, C, T, views per GPU, interpolation
-    "c2": dict(shape="nascar", scale=0.6, dy=0.25, H=512, W=512, C=3, T=1024, B=8, interp="bilinear",
+    # B = views per GPU (weak scaling) or views in total (strong scaling: sharded over the ranks)
+    "c2": dict(shape="nascar", scale=0.6, dy=0.25, H=512, W=512, C=3, T=1024, B=8, interp="bilinear", flavour="lp",
+               scaling="weak",
                label="configs[1]: nascar.obj F=7500, 3ch 1024^2 texture, 512x512, 8 views/GPU, latent_paint flavour, bilinear"),
-    "c1": dict(shape="blub", scale=0.6, dy=0.25, H=64, W=64, C=4, T=128, B=1, interp="nearest",
+    "c1": dict(shape="blub", scale=0.6, dy=0.25, H=64, W=64, C=4, T=128, B=1, interp="nearest", flavour="lp",
+               scaling="weak",
                label="configs[0]: blub.obj F=14208, 4ch 128^2 latent texture, 64x64, 1 view, nearest"),
+    "c3": dict(shape="teddy", scale=1.0, dy=0.0, H=64, W=64, C=4, T=512, B=64, interp="bilinear", flavour="mesh",
+               scaling="strong",
+               label="configs[2]: teddy.obj F=5760, 4ch 512^2 latent texture, 64x64 (train_grid_size), 64 views in total "
+                     "sharded over the GPUs, latent_paint_mesh flavour (body camera), bilinear"),
+    "c4": dict(shape="sphere", subdivide=5, scale=0.6, dy=0.25, H=1024, W=1024, C=3, T=1024, B=16, interp="bilinear",
+               flavour="lp", scaling="weak",
+               label="configs[3]: sphere.obj subdivided 5x F=1310720, 3ch 1024^2 texture, 1024x1024, 16 views/GPU, "
+                     "latent_paint flavour, bilinear"),
 }
-FOV = np.pi / 3
+FOV = np.pi / 3                       # latent_paint flavour (render.py:11)
+FOV_BODY, LOOK_AT_BODY = np.pi / 4, -0.3   # latent_paint_mesh flavour, body camera (render.py:18-19, 33)
 
 
-def algorithmic_bytes(V, F, H, W, C, T, B):
-    """SURVEY.md §8(d) / BASELINE.md §3, split per kernel (DESIGN.md 'Algorithmic bytes')."""
-    fwd = B * (12 * V + 36 * F + H * W * (4 * C + 12)) + 4 * C * T * T
+def algorithmic_bytes(V, F, H, W, C, T, B, flavour="lp"):
+    """SURVEY.md §8(d) / BASELINE.md §3, split per kernel (DESIGN.md 'Algorithmic bytes'); the mesh flavour adds
+    normals (12) + lighting (4) bytes per pixel to the forward."""
+    fwd = B * (12 * V + 36 * F + H * W * (4 * C + 12 + (16 if flavour == "mesh" else 0))) + 4 * C * T * T
     bwd = B * (H * W * (4 * C + 8)) + 4 * C * T * T
     return fwd, bwd
 
 
-def make_views(B, seed):
+def make_views(B, seed, flavour="lp"):
+    """radius, theta, phi drawn in the reference's order (views_dataset.py:16-18 / :22-24)."""
     g = torch.Generator().manual_seed(seed)
-    radius = torch.rand(B, generator=g) * 0.5 + 1.0
-    theta = torch.deg2rad(torch.rand(B, generator=g) * 135.0 + 15.0)
+    if flavour == "mesh":                         # latent_paint_mesh train_config.py:18-22
+        radius = torch.rand(B, generator=g) * 1.0 + 1.4
+        theta = torch.deg2rad(torch.rand(B, generator=g) * 50.0 + 60.0)
+    else:                                         # latent_paint views_dataset.py:9 (theta from 15 deg: SURVEY.md 8d)
+        radius = torch.rand(B, generator=g) * 0.5 + 1.0
+        theta = torch.deg2rad(torch.rand(B, generator=g) * 135.0 + 15.0)
     phi = torch.deg2rad(torch.rand(B, generator=g) * 360.0)
     return radius, theta, phi
 
@@ -65,8 +87,15 @@ def cameras_for(radius, theta, phi, dy):
     return torch.cat([lp.camera.camera_from_view(theta[i], phi[i], float(radius[i]), dy) for i in range(len(theta))]).contiguous()
 
 
+def workload_cameras(w, B, seed):
+    radius, theta, phi = make_views(B, seed, w.get("flavour", "lp"))
+    return cameras_for(radius, theta, phi, LOOK_AT_BODY if w.get("flavour") == "mesh" else w["dy"])
+
+
 def load_scene(w):
     m = lp.meshio.find_shape(w["shape"])
+    if w.get("subdivide"):
+        m = lp.meshio.subdivide(m, w["subdivide"])
     verts = lp.meshio.normalize_vertices(m.vertices, w["scale"], w["dy"])
     return verts, m.faces, lp.meshio.face_uv_attributes(m)
 
@@ -77,11 +106,14 @@ def render_forward_raster_fused(fwd, stream):
 
 
 class DeviceStep:
-    """One buffer set + the two C-ABI argument blocks of a fwd+bwd step on resident inputs."""
+    """One buffer set + the two C-ABI argument blocks of a fwd+bwd step on resident inputs.
+    ``w['flavour']``: 'lp' = latent_paint Renderer (masked image, fov pi/3), 'mesh' = latent_paint_mesh Renderer
+    (unmasked image, float mask, normals + SH lighting outputs, nz == 0 culling, body camera)."""
 
     def __init__(self, geom, w, cams, seed, device, grad_tex=None, accum=None):
         verts, faces, uv = geom
         B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
+        mesh_flavour = w.get("flavour", "lp") == "mesh"
         self.device = device
         self.tex = (0.4 * torch.randn(1, C, T, T, generator=torch.Generator().manual_seed(seed))).to(device)
         self.grad_image = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(seed + 1)).to(device)
@@ -96,17 +128,30 @@ class DeviceStep:
         a = _lib.LpForwardArgs()
         a.verts, a.faces, a.V, a.F = verts.data_ptr(), faces.data_ptr(), verts.shape[0], faces.shape[0]
         a.cameras, a.B, a.H, a.W = self.cams.data_ptr(), B, H, W
-        p = 1.0 / np.tan(FOV / 2)
+        p = 1.0 / np.tan((FOV_BODY if mesh_flavour else FOV) / 2)
         a.proj[0], a.proj[1], a.proj[2] = p, p, -1.0
         a.multiplier, a.eps = 1000.0, 1e-8
-        a.flags = _lib.LP_FLAG_MASK_IMAGE | _lib.LP_FLAG_REJECT_BEHIND
+        a.flags = (_lib.LP_FLAG_CULL_NZ_ZERO if mesh_flavour else _lib.LP_FLAG_MASK_IMAGE) | _lib.LP_FLAG_REJECT_BEHIND
         a.face_uv, a.texture = uv.data_ptr(), self.tex.data_ptr()
         a.C, a.Th, a.Tw = C, T, T
         a.interp = _lib.LP_INTERP_BILINEAR if w["interp"] == "bilinear" else _lib.LP_INTERP_NEAREST
         a.image, a.mask, a.uv = self.image.data_ptr(), self.mask.data_ptr(), self.uv.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
         a.tile_any = self.tile_any.data_ptr()
-        if os.environ.get("LP_DEBUG_FWD_STOP"):
+        self.keep = [verts, faces, uv]
+        if mesh_flavour:
+            V, F = verts.shape[0], faces.shape[0]
+            off, vf = lp.functional.vertex_face_csr(faces, V)
+            self.fn = torch.empty(B, F, 3, device=device)
+            self.vn = torch.empty(B, V, 3, device=device)
+            self.normals = torch.empty(B, 3, H, W, device=device)
+            self.lighting = torch.empty(B, 1, H, W, device=device)
+            self.lights = torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0], device=device)
+            a.vf_offsets, a.vf_faces = off.data_ptr(), vf.data_ptr()
+            a.face_normals, a.vertex_normals = self.fn.data_ptr(), self.vn.data_ptr()
+            a.lights, a.normals, a.lighting = self.lights.data_ptr(), self.normals.data_ptr(), self.lighting.data_ptr()
+            self.keep += [off, vf]
+        if os.environ.get("LP_DEBUG_FWD_STOP"):      # only honoured by -DLP_PROFILE builds (tools/)
             a.flags |= 1 << int(os.environ["LP_DEBUG_FWD_STOP"])
         b = _lib.LpBackwardArgs()
         b.B, b.H, b.W, b.flags = B, H, W, a.flags & 0xff
@@ -122,20 +167,16 @@ class DeviceStep:
             b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE | _lib.LP_FLAG_GRAD_INTERLEAVED
         else:
             self.accum = torch.empty(int(L.lp_backward_workspace_bytes(C, T, T)), dtype=torch.uint8, device=device)
-        if accum is not None:
-            pass
-        elif self.accum.numel() and os.environ.get("LP_BWD_VEC", "1") == "1":
-            b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
-            b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
-        else:
-            self.accum = self.accum[:0]
-        if os.environ.get("LP_DEBUG_NO_ATOMICS") == "1":
-            b.flags |= 1 << 30
+            if self.accum.numel() and os.environ.get("LP_BWD_VEC", "1") == "1":
+                b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
+                b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
+            else:
+                self.accum = self.accum[:0]
         if os.environ.get("LP_DEBUG_BWD_STOP"):
             b.flags |= 1 << int(os.environ["LP_DEBUG_BWD_STOP"])
         self.fwd, self.bwd = a, b
-        self.keep = (verts, faces, uv)
         self.launches = 0
+        self.launches_prepare = 0
 
     def prepare(self, stream, with_raster):
         """The texture-independent stages of this set's views on `stream` (a raw cudaStream_t handle):
@@ -167,6 +208,12 @@ class DeviceStep:
         _lib.check(L.lp_render_backward(ctypes.byref(self.bwd), stream))
         self.launches = self.launches_prepare + n + L.lp_last_launch_count()
 
+    def run_split(self, stream=None):
+        """prepare -> raster -> shade -> backward on one stream: the benched kernels, serially (tests use it)."""
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if stream is None else stream
+        self.prepare(stream, True)
+        self.shade_backward(stream, torch.cuda.current_stream(self.device), True)
+
     def run(self):
         """Enqueue forward, zero the gradient, backward on torch's current stream."""
         L = _lib.lib()
@@ -183,12 +230,12 @@ class HostStep:
     """The reference-facing call with HOST buffers: pinned cameras / upstream gradient in, pinned
     image / mask / texture gradient out, through ``lp_render_step_host`` (tests use it too)."""
 
-    def __init__(self, verts, faces, uv, texture, B, H, W, interp, fov, device="cuda:0"):
+    def __init__(self, verts, faces, uv, texture, B, H, W, interp, fov, device="cuda:0", flavour="lp"):
         self.device = torch.device(device)
         geom = (verts.to(self.device).float().contiguous(), faces.to(self.device, torch.int32).contiguous(),
                 uv.to(self.device).float().reshape(-1, 3, 2).contiguous())
         C, T = texture.shape[1], texture.shape[-1]
-        w = dict(B=B, H=H, W=W, C=C, T=T, interp=interp)
+        w = dict(B=B, H=H, W=W, C=C, T=T, interp=interp, flavour=flavour)
         self.dev = DeviceStep(geom, w, torch.zeros(B, 4, 3), 0, self.device)
         self.dev.tex.copy_(texture.reshape(1, C, T, T))
         self.h_cams = torch.empty(B, 4, 3).pin_memory()
@@ -252,24 +299,40 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference_views_per_s(w, n_views, seed=0, warmup=0, impl="torch"):
     """The oracle port of the reference CPU path: reference glue mirror over the torch kaolin
-    restatement (rasterizer in torch, all host threads), forward + backward, one view per call as
-    in the reference's latent_paint Renderer."""
+    restatement (rasterizer in torch, all host threads), forward + backward; one view per call for the
+    latent_paint Renderer, batches of up to 8 views for the (batched) latent_paint_mesh Renderer."""
     from oracle import kaolin_shim, renderer_ref
     kaolin_shim.RASTER_IMPL = impl
     torch.set_num_threads(os.cpu_count() or 1)
     verts, faces, uv = load_scene(w)
     tex = (0.4 * torch.randn(1, w["C"], w["T"], w["T"], generator=torch.Generator().manual_seed(seed))).requires_grad_(True)
-    grad = torch.randn(1, w["C"], w["H"], w["W"], generator=torch.Generator().manual_seed(seed + 1))
-    radius, theta, phi = make_views(warmup + n_views, seed)
-    r = renderer_ref.LatentPaintRendererRef(dim=(w["W"], w["H"]), interpolation_mode=w["interp"])
+    flavour = w.get("flavour", "lp")
+    radius, theta, phi = make_views(warmup + n_views, seed, flavour)
     t0 = None
-    for i in range(warmup + n_views):
-        if i == warmup:
-            t0 = time.perf_counter()
-        tex.grad = None
-        image, _ = r.render_single_view_texture(verts, faces, uv, tex, elev=float(theta[i]), azim=float(phi[i]),
-                                                radius=float(radius[i]), look_at_height=w["dy"])
-        image.backward(grad)
+    if flavour == "mesh":
+        r = renderer_ref.LatentPaintMeshRendererRef(dim=(w["W"], w["H"]))
+        per = 8
+        i = 0
+        while i < warmup + n_views:
+            if t0 is None and i >= warmup:
+                t0 = time.perf_counter()
+            j = min(i + per, warmup + n_views)
+            grad = torch.randn(j - i, w["C"], w["H"], w["W"], generator=torch.Generator().manual_seed(seed + 1))
+            tex.grad = None
+            outs = r.render_single_view_texture(verts, faces, uv, tex, theta[i:j], phi[i:j], radius[i:j],
+                                                dims=(w["W"], w["H"]), is_body=True)
+            outs[0].backward(grad)
+            i = j
+    else:
+        grad = torch.randn(1, w["C"], w["H"], w["W"], generator=torch.Generator().manual_seed(seed + 1))
+        r = renderer_ref.LatentPaintRendererRef(dim=(w["W"], w["H"]), interpolation_mode=w["interp"])
+        for i in range(warmup + n_views):
+            if i == warmup:
+                t0 = time.perf_counter()
+            tex.grad = None
+            image, _ = r.render_single_view_texture(verts, faces, uv, tex, elev=float(theta[i]), azim=float(phi[i]),
+                                                    radius=float(radius[i]), look_at_height=w["dy"])
+            image.backward(grad)
     dt = time.perf_counter() - t0
     return n_views / dt, dt
 
@@ -278,15 +341,16 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = w["B"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = w["B"] // world if w["scaling"] == "strong" else w["B"]
     # each step = one batch of B views on the CPU (≈0.2 s/view on 8 cores for c2)
     total = (args.warmup + args.steps) * B
-    cap = 400                                        # bound the run to a few minutes
+    cap = 400 if w["H"] <= 512 else 24                  # bound the run to a few minutes
     per_step = B if total <= cap else max(1, cap // (args.warmup + args.steps))
     vps, dt = cpu_reference_views_per_s(w, args.steps * per_step, warmup=args.warmup * per_step)
     line = {"metric": "views/sec (fwd+bwd render)", "value": vps, "unit": "views/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "views_per_step": per_step},
             "cpu_baseline": {"value": vps, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": f"{args.steps} steps x {per_step} views, torch CPU path of the oracle "
@@ -295,54 +359,55 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster", "deep"],
-                    help="overlap texture-independent stages of later steps with step k on other streams: 'geometry' = setup + "
-                         "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1), 'deep' = three stages on three "
-                         "streams (geometry | visibility/uv | texture fetch + backward + exchange); auto = deep")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
-                    help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
-                         "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
-    ap.add_argument("--cpu-views", type=int, default=160, help="views timed for cpu_baseline, about 10-30 s of CPU work (0 = skip)")
-    args = ap.parse_args()
-    w = WORKLOADS[args.workload]
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args, w)
+class Env:
+    """Process-wide state of one bench run: rank / world, device, the process group."""
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the render path has no CPU implementation (use --impl reference)")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    device = torch.device("cuda", local)
-    torch.cuda.set_device(device)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = torch.device("cuda", self.local)
+        torch.cuda.set_device(self.device)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.device)
+            self.dist = dist
 
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.device)
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(args, env, w, full):
+    """Time ``args.steps`` steps of workload ``w`` (max over ranks).  ``full``: also the roofline, e2e and
+    cpu_baseline legs.  Returns the pieces of the JSON line."""
+    world, rank, device, dist = env.world, env.rank, env.device, env.dist
     verts, faces, uv = load_scene(w)
     geom = (verts.to(device).float().contiguous(), faces.to(device, torch.int32).contiguous(),
             uv.to(device).float().reshape(-1, 3, 2).contiguous())
-    B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
+    strong = w["scaling"] == "strong"
+    if strong and w["B"] % world:
+        raise SystemExit(f"bench.py: {w['B']} views do not shard evenly over {world} ranks")
+    B = w["B"] // world if strong else w["B"]
+    w = dict(w, B=B)                                      # per-rank batch from here on
+    H, W, C, T = w["H"], w["W"], w["C"], w["T"]
     V, F = verts.shape[0], faces.shape[0]
+    flavour = w.get("flavour", "lp")
+    n_sets = args.sets
     sets, symm_bufs, allreduce_mode = [], [], "none" if world == 1 else "nccl"
-    if args.allreduce == "auto":        # measured: inside the step graph the two-shot peer kernels win at
-        args.allreduce = "multimem" if world >= 4 else "p2p"      # 2 GPUs, the in-switch kernel from 4 GPUs up
-        auto_allreduce = True
-    else:
-        auto_allreduce = False
-    if world > 1 and args.allreduce != "nccl":
+    allreduce = args.allreduce
+    if allreduce == "auto":             # measured (DESIGN.md §6): inside the step graph the two-shot peer kernels win at
+        allreduce = "multimem" if world >= 4 else "p2p"           # 2 GPUs, the in-switch kernel from 4 GPUs up
+    if world > 1 and allreduce != "nccl":
         from latent_nerf_test_b200.parallel import SymmetricGradientBuffer
         want_fused = C <= 4 and os.environ.get("LP_EXCHANGE_FUSED", "1") == "1"
         # attempts, best first: exchange fused with the unpack, then unpack + all-reduce of the planar gradient over
@@ -351,11 +416,11 @@ def main():
             err = None
             try:
                 symm_bufs = []
-                for s in range(args.sets):
+                for s in range(n_sets):
                     sb = SymmetricGradientBuffer(C * T * T, device, interleaved_texels=T * T if fused else 0, channels=C)
-                    if args.allreduce == "p2p":
+                    if allreduce == "p2p":
                         sb.mode = "p2p"
-                    elif args.allreduce == "multimem" and sb.mode != "multimem":
+                    elif allreduce == "multimem" and sb.mode != "multimem":
                         raise RuntimeError("no multicast support on this box")
                     symm_bufs.append(sb)
                 gen = torch.Generator(device=device).manual_seed(rank)
@@ -380,11 +445,10 @@ def main():
                 break
             print(f"bench.py: {'fused ' if fused else ''}symmetric-memory exchange unavailable ({err}); trying the next form", file=sys.stderr)
             symm_bufs, allreduce_mode = [], "nccl"
-    for s in range(args.sets):
-        radius, theta, phi = make_views(B, 1000 * rank + s)
+    for s in range(n_sets):
         gt = symm_bufs[s].view((C, T, T)) if symm_bufs else None
         acc = symm_bufs[s].accum if symm_bufs and symm_bufs[s].fused else None
-        sets.append(DeviceStep(geom, w, cameras_for(radius, theta, phi, w["dy"]), 10 * s + 1, device, grad_tex=gt, accum=acc))
+        sets.append(DeviceStep(geom, w, workload_cameras(w, B, 1000 * rank + s), 10 * s + 1, device, grad_tex=gt, accum=acc))
     set_bytes = sum(t.numel() * t.element_size() for t in (sets[0].tex, sets[0].grad_image, sets[0].image, sets[0].mask,
                                                            sets[0].uv, sets[0].grad_tex))
 
@@ -409,18 +473,19 @@ def main():
     # --pipeline: the texture-independent stages of the next step (geometry, bins, visibility, uv) run on a
     # second stream while the current step fetches the texture, back-propagates (and all-reduces); each
     # buffer set has its own workspace and saved-uv buffer
-    if args.pipeline == "auto":       # measured: 82 us/step deep vs 89 geometry vs 102 raster at N = 1; 123 vs 138 vs 124 at N = 2
-        args.pipeline = "deep"
-    pipe_deep = args.pipeline == "deep"
-    pipe_raster = args.pipeline == "raster" or pipe_deep
-    args.pipeline = None if args.pipeline == "off" else args.pipeline
-    prep_stream = torch.cuda.Stream(device) if args.pipeline else None
+    pipeline = args.pipeline
+    if pipeline == "auto":
+        pipeline = "deep"
+    pipe_deep = pipeline == "deep"
+    pipe_raster = pipeline == "raster" or pipe_deep
+    pipeline = None if pipeline == "off" else pipeline
+    prep_stream = torch.cuda.Stream(device) if pipeline else None
     rast_stream = torch.cuda.Stream(device) if pipe_deep else None
     geom_done = [torch.cuda.Event() for _ in sets]
     prep_done = [torch.cuda.Event() for _ in sets]
     set_free = [torch.cuda.Event() for _ in sets]
     pipe_state = {"primed": [False] * len(sets)}
-    h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if args.pipeline else None
+    h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if pipeline else None
     h_rast = ctypes.c_void_p(rast_stream.cuda_stream) if pipe_deep else None
     h_main = ctypes.c_void_p(stream.cuda_stream)
 
@@ -453,13 +518,13 @@ def main():
         pipe_state["primed"][k] = True
         return k
 
-    # the same pipeline captured once as a CUDA graph of PIPE_STEPS steps (two capture streams, event edges)
+    # the same pipeline captured once as a CUDA graph of PIPE_STEPS steps (capture streams joined by event edges);
     # one replay = PIPE_STEPS steps; the pipeline drains between replays, so a replay is made long
     PIPE_STEPS = len(sets) * max(2, min(10, args.steps // len(sets)))
     if os.environ.get("LP_PIPE_STEPS"):
         PIPE_STEPS = len(sets) * max(1, int(os.environ["LP_PIPE_STEPS"]) // len(sets))
     pipe_graph = None
-    if args.pipeline and not args.no_graph and (world == 1 or symm_bufs):
+    if pipeline and not args.no_graph and (world == 1 or symm_bufs):
         try:
             with torch.cuda.stream(stream):
                 for i in range(PIPE_STEPS):                     # warm both paths before capture
@@ -487,7 +552,7 @@ def main():
     def local_step(i):
         """One step without the exchange (rank-local keep-busy loop)."""
         k = i % len(sets)
-        if args.pipeline:
+        if pipeline:
             return pipelined_step(i, with_exchange=False)
         if graphs is not None:
             graphs[k].replay()
@@ -496,43 +561,45 @@ def main():
         return k
 
     def one_step(i):
-        if args.pipeline:
+        if pipeline:
             pipelined_step(i)
         else:
             exchange(local_step(i))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(device)
+    def run_steps(n):
+        """n steps the way the timed region runs them: whole replays of the pipelined graph, the rest eagerly."""
+        if pipe_graph is not None:
+            for _ in range(n // PIPE_STEPS):
+                pipe_graph.replay()
+            n = n % PIPE_STEPS
+        for i in range(n):
+            one_step(i)
 
     with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            one_step(i)
-        barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        # warm-up: at least `warmup` steps AND at least one replay of every graph the timed region replays, so the
+        # first (slow: upload + first-launch initialisation) replay is outside the timed region
+        run_steps(max(args.warmup, PIPE_STEPS if pipe_graph is not None else 0))
+        if pipeline:
+            stream.wait_stream(prep_stream)
+        if pipe_deep:
+            stream.wait_stream(rast_stream)
+        env.barrier()
+        sampler = ClockSampler(env.local) if rank == 0 and full else None
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        if args.pipeline:
+        if pipeline:
             prep_stream.wait_event(e0)
         if pipe_deep:
             rast_stream.wait_event(e0)
-        if pipe_graph is not None:
-            for _ in range(args.steps // PIPE_STEPS):
-                pipe_graph.replay()
-            for i in range(args.steps % PIPE_STEPS):
-                one_step(i)
-        else:
-            for i in range(args.steps):
-                one_step(i)
-        if args.pipeline:
+        run_steps(args.steps)
+        if pipeline:
             stream.wait_stream(prep_stream)
         if pipe_deep:
             stream.wait_stream(rast_stream)
         e1.record(stream)
-        barrier()
+        env.barrier()
         ms = e0.elapsed_time(e1)
         # keep the GPU busy a little longer if the region was too short for nvidia-smi to sample it
         if sampler and ms < 400:
@@ -542,13 +609,52 @@ def main():
                     local_step(i)              # no collective here: the other ranks are not in this loop
                 torch.cuda.synchronize(device)
         clocks = sampler.summary() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = env.max_over_ranks(ms)
     value = world * B * args.steps / (ms * 1e-3)
+    res = {"value": value, "ms": ms, "B": B, "clocks": clocks, "launches_per_step": sets[0].launches,
+           "allreduce_mode": allreduce_mode, "pipeline": pipeline or "off",
+           "cuda_graph": (graphs is not None and not pipeline) or pipe_graph is not None,
+           "l2": f"{len(sets)} rotating buffer sets of {set_bytes / 1e6:.0f} MB each "
+                 f"({len(sets) * set_bytes / 1e6:.0f} MB > 126 MB L2): inputs larger than L2"
+                 if len(sets) * set_bytes > 126e6 else
+                 f"{len(sets)} rotating buffer sets of {set_bytes / 1e6:.1f} MB each ({len(sets) * set_bytes / 1e6:.0f} MB: "
+                 f"fits the 126 MB L2 — this workload is L2-resident by nature)",
+           "roofline": None, "e2e": None, "cpu": None}
+    if not full:
+        return res
 
-    line = None
+    # ---- e2e: host buffers through lp_render_step_host, on every rank at once
+    if not args.no_e2e:
+        # three host-buffer contexts in flight on three streams: the H2D copy of one step, the kernels of the
+        # previous and the D2H copy of the one before overlap; every step still moves all its bytes both ways
+        n_ctx = 3
+        ctxs, streams_e2e = [], [torch.cuda.Stream(device) for _ in range(n_ctx)]
+        for j in range(n_ctx):
+            hs = HostStep(verts, faces, uv, sets[0].tex.cpu(), B, H, W, w["interp"], FOV, device=str(device), flavour=flavour)
+            hs.h_cams.copy_(workload_cameras(w, B, 77 + j + 10 * rank))
+            hs.h_grad.copy_(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5 + j)))
+            ctxs.append(hs)
+        n_e2e = max(6, min(args.steps, 60))
+        for j in range(2 * n_ctx):
+            ctxs[j % n_ctx].step_async(streams_e2e[j % n_ctx])
+        env.barrier()
+        t0 = time.perf_counter()
+        for j in range(n_e2e):
+            streams_e2e[j % n_ctx].synchronize()          # the context's previous results have landed on the host
+            ctxs[j % n_ctx].step_async(streams_e2e[j % n_ctx])
+        torch.cuda.synchronize(device)
+        e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+        hs = ctxs[0]
+        t1 = time.perf_counter()
+        for _ in range(5):
+            hs.step()
+        sync_ms = 1e3 * (time.perf_counter() - t1) / 5
+        res["e2e"] = {"value": world * B * n_e2e / e2e_s, "unit": "views/s", "h2d_bytes_per_step": hs.h2d_bytes,
+                      "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": 1e3 * e2e_s / n_e2e, "n_gpus": world,
+                      "bytes_are": "per rank and step", "in_flight": n_ctx, "ms_per_step_one_at_a_time": sync_ms}
+        del ctxs
+        env.barrier()
+
     if rank == 0:
         # ---- roofline: instrumented eager pass over the same steps (events around every kernel)
         L = _lib.lib()
@@ -565,7 +671,7 @@ def main():
             timings = _lib.collect_timings()
             L.lp_timing_enable(0)
         per_kernel = {k: 1e3 * v[0] / v[1] for k, v in timings.items()}           # µs per launch
-        fwd_bytes, bwd_bytes = algorithmic_bytes(V, F, H, W, C, T, B)
+        fwd_bytes, bwd_bytes = algorithmic_bytes(V, F, H, W, C, T, B, flavour)
         if pipe_raster:
             # split forward: the tile kernel writes mask + saved uv only; k_shade reads the uv and the texture and
             # writes the image (its uv read is extra traffic the fused form does not have, so not counted)
@@ -579,73 +685,85 @@ def main():
         kb = {"k_raster_shade": fwd_bytes_tile if pipe_raster else fwd_bytes, "k_backward_texture": bwd_bytes}
         if pipe_raster:
             kb["k_shade"] = shade_bytes
+        kb = {k: v for k, v in kb.items() if k in per_kernel}
         dom = max(kb, key=lambda k: per_kernel.get(k, 0.0))
         achieved = kb[dom] / (per_kernel[dom] * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")                       # dram bytes per launch from ncu --set full
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and args.workload == "c2":
             traffic = json.load(open(tp)).get(dom + ("_split" if pipe_raster and dom == "k_raster_shade" else ""))
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": kb[dom], "us_per_launch": per_kernel[dom],
-                    "kernels_us": per_kernel,
-                    "step": {"algorithmic_bytes": fwd_bytes + bwd_bytes,
-                             "achieved_gbs": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9,
-                             "frac": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9 / peak}}
-
-        # ---- e2e: host buffers through lp_render_step_host
-        e2e = None
-        if not args.no_e2e:
-            # three host-buffer contexts in flight on three streams: the H2D copy of one step, the kernels of the
-            # previous and the D2H copy of the one before overlap; every step still moves all its bytes both ways
-            n_ctx = 3
-            ctxs, streams_e2e = [], [torch.cuda.Stream(device) for _ in range(n_ctx)]
-            for j in range(n_ctx):
-                hs = HostStep(verts, faces, uv, sets[0].tex.cpu(), B, H, W, w["interp"], FOV, device=str(device))
-                radius, theta, phi = make_views(B, 77 + j)
-                hs.h_cams.copy_(cameras_for(radius, theta, phi, w["dy"]))
-                hs.h_grad.copy_(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(5 + j)))
-                ctxs.append(hs)
-            n_e2e = max(6, min(args.steps, 60))
-            for j in range(2 * n_ctx):
-                ctxs[j % n_ctx].step_async(streams_e2e[j % n_ctx])
-            torch.cuda.synchronize(device)
-            t0 = time.perf_counter()
-            for j in range(n_e2e):
-                streams_e2e[j % n_ctx].synchronize()          # the context's previous results have landed on the host
-                ctxs[j % n_ctx].step_async(streams_e2e[j % n_ctx])
-            torch.cuda.synchronize(device)
-            e2e_s = time.perf_counter() - t0
-            hs = ctxs[0]
-            t1 = time.perf_counter()
-            for _ in range(5):
-                hs.step()
-            sync_ms = 1e3 * (time.perf_counter() - t1) / 5
-            e2e = {"value": B * n_e2e / e2e_s, "unit": "views/s", "h2d_bytes_per_step": hs.h2d_bytes,
-                   "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": 1e3 * e2e_s / n_e2e, "n_gpus": 1,
-                   "in_flight": n_ctx, "ms_per_step_one_at_a_time": sync_ms}
+        res["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": kb[dom], "us_per_launch": per_kernel[dom],
+                           "kernels_us": per_kernel,
+                           "step": {"algorithmic_bytes": fwd_bytes + bwd_bytes,
+                                    "achieved_gbs": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9,
+                                    "frac": (fwd_bytes + bwd_bytes) / (ms * 1e-3 / args.steps) / 1e9 / peak}}
 
         # ---- cpu baseline: bounded sample of the same workload on the host cores
-        cpu = None
         if args.cpu_views > 0 and world == 1:
-            vps, dt = cpu_reference_views_per_s(w, args.cpu_views, warmup=2)
-            cpu = {"value": vps, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"{args.cpu_views} views of the same workload, one view per call, {dt:.1f} s; oracle torch CPU path"}
+            n_cpu = args.cpu_views if H <= 512 else min(args.cpu_views, 8)
+            vps, dt = cpu_reference_views_per_s(w, n_cpu, warmup=2)
+            res["cpu"] = {"value": vps, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+                          "sample": f"{n_cpu} views of the same workload, {dt:.1f} s; oracle torch CPU path"}
+    return res
 
-        launches_per_step = sets[0].launches
-        line = {"metric": "views/sec (fwd+bwd render)", "value": value, "unit": "views/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w["label"], "views_per_gpu_per_step": B, "cuda_graph": (graphs is not None and not args.pipeline) or pipe_graph is not None, "pipeline": args.pipeline or "off",
-                           "l2": f"{len(sets)} rotating buffer sets of {set_bytes / 1e6:.0f} MB each "
-                                 f"({len(sets) * set_bytes / 1e6:.0f} MB > 126 MB L2): inputs larger than L2",
-                           "parallelism": f"views sharded over {world} GPU(s)" + (f", all-reduce of the texture gradient each step ({allreduce_mode})" if world > 1 else "")},
-                "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster", "deep"],
+                    help="overlap texture-independent stages of later steps with step k on other streams: 'geometry' = setup + "
+                         "bins, 'raster' = also visibility/uv (hides the all-reduce when N > 1), 'deep' = three stages on three "
+                         "streams (geometry | visibility/uv | texture fetch + backward + exchange); auto = deep")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
+                    help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
+                         "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the configs[2] strong-scaling measurement of the default run")
+    ap.add_argument("--cpu-views", type=int, default=160, help="views timed for cpu_baseline, about 10-30 s of CPU work (0 = skip)")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args, w)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU implementation (use --impl reference)")
+    env = Env()
+    res = measure(args, env, w, full=True)
+    strong = None
+    if args.workload == "c2" and not args.no_strong and WORKLOADS["c3"]["B"] % env.world == 0:
+        # BASELINE.json configs[2] beside the weak-scaling line: 64 teddy views in total, sharded over the ranks
+        sres = measure(args, env, WORKLOADS["c3"], full=False)
+        strong = {"workload": WORKLOADS["c3"]["label"], "scaling": "strong", "value": sres["value"], "unit": "views/s",
+                  "n_gpus": env.world, "views_total": WORKLOADS["c3"]["B"], "views_per_gpu_per_step": sres["B"],
+                  "ms_per_step": sres["ms"] / args.steps, "steps": args.steps,
+                  "exchange_payload_bytes": 4 * WORKLOADS["c3"]["C"] * WORKLOADS["c3"]["T"] ** 2,
+                  "allreduce": sres["allreduce_mode"], "launches_per_step": sres["launches_per_step"]}
+    line = None
+    if env.rank == 0:
+        world = env.world
+        line = {"metric": "views/sec (fwd+bwd render)", "value": res["value"], "unit": "views/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"] / args.steps, "higher_is_better": True,
+                "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["label"], "views_per_gpu_per_step": res["B"], "cuda_graph": res["cuda_graph"],
+                           "pipeline": res["pipeline"], "l2": res["l2"],
+                           "parallelism": f"views sharded over {world} GPU(s)" + (f", all-reduce of the texture gradient each step ({res['allreduce_mode']})" if world > 1 else "")},
+                "gpu_launches": res["launches_per_step"] * args.steps, "launches_per_step": res["launches_per_step"],
+                "clocks": res["clocks"], "roofline": res["roofline"], "e2e": res["e2e"], "cpu_baseline": res["cpu"],
+                "strong_scaling": strong}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return line
 
 

@@ -70,10 +70,12 @@ enum {
                                            (Renderer.render_single_view, latent_paint render.py:34-47) */
     LP_FLAG_GRAD_OVERWRITE   = 1u << 5, /* lp_render_backward with a workspace: grad_texture is written, not
                                            accumulated into, so the caller need not zero it */
-    LP_FLAG_GRAD_INTERLEAVED = 1u << 6  /* lp_render_backward with a workspace: leave the gradient in the workspace as
+    LP_FLAG_GRAD_INTERLEAVED = 1u << 6, /* lp_render_backward with a workspace: leave the gradient in the workspace as
                                            (Th,Tw,4) texel-interleaved float4 and do not touch grad_texture —
                                            lp_allreduce_unpack sums it over the ranks and writes the planar gradient */
-    /* bits 20-30 are profiling switches of bench.py (stop-after-stage ablations), not part of the contract */
+    LP_FLAG_MICRO_OFF        = 1u << 22, /* never / always rasterize small faces face-parallel in the setup kernel */
+    LP_FLAG_MICRO_ON         = 1u << 23  /* (default: on when the mesh has at least one face per 16 pixels) */
+    /* bits 24-30: stop-after-stage ablation switches, compiled in only with -DLP_PROFILE (tools/), ignored otherwise */
 };
 
 typedef struct LpForwardArgs {
@@ -113,7 +115,7 @@ typedef struct LpForwardArgs {
     float         *image;          /* (B,C|D,H,W) */
     float         *mask;           /* (B,1,H,W) */
     float         *uv;             /* (B,H,W,2) interpolated UVs, saved for lp_render_backward;
-                                      with LP_FLAG_MASK_IMAGE uncovered pixels hold u = -1 */
+                                      with LP_FLAG_MASK_IMAGE uncovered pixels hold u = NaN (coordinates may be negative) */
     int32_t       *face_idx;       /* (B,H,W) winning face, -1 = none */
     float         *bary;           /* (B,H,W,3) perspective-correct weights w' */
     float         *depth;          /* (B,H,W) camera-space z of the visible surface, 0 = none */

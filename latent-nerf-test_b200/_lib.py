@@ -30,6 +30,8 @@ LP_FLAG_CULL_NZ_ZERO = 1 << 3
 LP_FLAG_SHADE_FEATURES = 1 << 4
 LP_FLAG_GRAD_OVERWRITE = 1 << 5
 LP_FLAG_GRAD_INTERLEAVED = 1 << 6
+LP_FLAG_MICRO_OFF = 1 << 22
+LP_FLAG_MICRO_ON = 1 << 23
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",

@@ -44,10 +44,14 @@ def _require_cuda(t, name):
 
 
 def _workspace(device, nbytes):
-    ws = _workspaces.get(device)
+    """Scratch of the forward call, one buffer per (device, stream): two renders enqueued on two streams never share
+    it, and a buffer that is outgrown stays referenced by the autograd node that used it (``keep`` lists below) until
+    the caching allocator may hand it out again in stream order."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -55,27 +59,38 @@ def _f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
-def _faces_i32(faces, device):
-    """The reference carries faces as int64 (LongTensor); the kernels read int32.  Converted
-    once per (tensor, version)."""
+def _faces_i32(faces, device, num_vertices=None):
+    """The reference carries faces as int64 (LongTensor); the kernels read int32.  Converted once per source tensor:
+    the cache entry keeps the source alive and is matched by identity and version, so a recycled address can never
+    return another mesh's faces.  The index range is validated once, when the copy is made (a malformed mesh raises
+    here where kaolin's gather would)."""
     if faces.dtype == torch.int32 and faces.device == device and faces.is_contiguous():
         return faces
-    key = (faces.data_ptr(), faces._version, tuple(faces.shape), faces.dtype, str(device))
+    key = (id(faces), str(device))
     hit = _int32_cache.get(key)
-    if hit is None:
+    if hit is None or hit[0] is not faces or hit[1] != faces._version:
         if len(_int32_cache) > 16:
             _int32_cache.clear()
-        hit = faces.detach().to(device=device, dtype=torch.int32).contiguous()
+        conv = faces.detach().to(device=device, dtype=torch.int32).contiguous()
+        if conv.numel():
+            lo, hi = int(faces.min()), int(faces.max())
+            if lo < 0 or (num_vertices is not None and hi >= num_vertices):
+                raise ValueError(f"lp_b200: face indices span [{lo}, {hi}] but the mesh has {num_vertices} vertices")
+        hit = (faces, faces._version, conv, int(faces.max()) if conv.numel() else -1)
         _int32_cache[key] = hit
-    return hit
+    elif num_vertices is not None and hit[3] >= num_vertices:
+        raise ValueError(f"lp_b200: face index {hit[3]} out of range for {num_vertices} vertices")
+    return hit[2]
 
 
 def vertex_face_csr(faces_i32, num_vertices):
     """Vertex → incident-corner lists in the order the reference accumulates them in
     ``compute_vertex_normals`` (render.py:99-101): corner 0 of every face in face order, then
     corner 1, then corner 2.  One stable sort per mesh topology, cached."""
-    key = (faces_i32.data_ptr(), faces_i32._version, tuple(faces_i32.shape), num_vertices)
+    key = (id(faces_i32), num_vertices)
     hit = _csr_cache.get(key)
+    if hit is not None and (hit[2] is not faces_i32 or hit[3] != faces_i32._version):
+        hit = None
     if hit is None:
         if len(_csr_cache) > 16:
             _csr_cache.clear()
@@ -86,9 +101,9 @@ def vertex_face_csr(faces_i32, num_vertices):
         counts = torch.bincount(corner_major, minlength=num_vertices)
         off = torch.zeros(num_vertices + 1, dtype=torch.int32, device=faces_i32.device)
         off[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        hit = (off.contiguous(), vf)
+        hit = (off.contiguous(), vf, faces_i32, faces_i32._version)
         _csr_cache[key] = hit
-    return hit
+    return hit[0], hit[1]
 
 
 @dataclass
@@ -185,7 +200,10 @@ class _RenderTexture(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.tex_shape = tuple(texture.shape)
         ctx.save_for_backward(uv, tile_any)
-        outs = (image, mask, uv, face_idx, bary, depth, normals, lighting)
+        # the saved uv carries the kernels' own conventions (NaN on uncovered pixels of the masked flavour, tiles
+        # without coverage not written at all); what the caller sees is kaolin's: 0 where nothing is covered
+        uv_out = torch.where(face_idx[..., None] >= 0, uv, torch.zeros_like(uv)) if cfg.want_buffers else uv
+        outs = (image, mask, uv_out, face_idx, bary, depth, normals, lighting)
         ctx.mark_non_differentiable(*[o for o in outs[1:] if o is not None])
         return outs
 
@@ -360,7 +378,8 @@ def render_composed(texture, face_features, tex_cfg: RenderConfig, feat_cfg: Ren
 
 def render_texture(texture, cfg: RenderConfig):
     """→ (image (B,C,H,W), mask (B,1,H,W), uv (B,H,W,2), face_idx|None, bary|None, depth|None,
-    normals|None, lighting|None)."""
+    normals|None, lighting|None).  ``uv`` is meaningful only with ``cfg.want_buffers`` (then 0 on uncovered
+    pixels, like kaolin's interpolated features); otherwise it is the kernels' saved-for-backward buffer."""
     return _RenderTexture.apply(texture, cfg)
 
 

@@ -104,9 +104,19 @@ def texture_mapping(texture_coordinates, texture_maps, mode="nearest"):
     """(B,H,W,2), (B,C,T,T) → (B,H,W,C); gradients flow into ``texture_maps``."""
     B = texture_coordinates.shape[0]
     dims = texture_coordinates.shape[1:-1]
-    uv = texture_coordinates.reshape(B, -1, 1, 2)
-    out = functional.texture_map(uv, texture_maps, mode)               # (B,C,N,1)
-    return out.permute(0, 2, 3, 1).reshape(B, *dims, texture_maps.shape[1])
+    C = texture_maps.shape[1]
+    if texture_coordinates.dim() == 4:                                   # (B,H,W,2): the kernels' own layout
+        out = functional.texture_map(texture_coordinates, texture_maps, mode)            # (B,C,H,W)
+        return out.permute(0, 2, 3, 1)
+    # flat coordinate lists: fold N into rows of 32 (padded with zeros, whose output is dropped and whose
+    # upstream gradient is therefore zero), so the backward launches full warps on a legal grid
+    uv = texture_coordinates.reshape(B, -1, 2)
+    N = uv.shape[1]
+    rows = (N + 31) // 32
+    if rows * 32 != N:
+        uv = torch.cat([uv, uv.new_zeros(B, rows * 32 - N, 2)], dim=1)
+    out = functional.texture_map(uv.reshape(B, rows, 32, 2), texture_maps, mode)         # (B,C,rows,32)
+    return out.reshape(B, C, rows * 32)[:, :, :N].permute(0, 2, 1).reshape(B, *dims, C)
 
 
 SH_BAND1_AXES = (1, 2, 0)        # BASELINE.md decree 5

@@ -51,7 +51,7 @@ class Renderer:
         cam = self.get_camera_from_view(torch.tensor(elev), torch.tensor(azim), r=radius,
                                         look_at_height=look_at_height).to(self.device)
         return functional.RenderConfig(
-            verts=functional._f32(verts, self.device), faces=functional._faces_i32(faces, self.device),
+            verts=functional._f32(verts, self.device), faces=functional._faces_i32(faces, self.device, verts.shape[0]),
             cameras=cam.contiguous(), proj=self._proj, H=int(dims[1]), W=int(dims[0]),
             flags=self._flags(white_background), interp=self.interpolation_mode, want_buffers=self.keep_buffers)
 

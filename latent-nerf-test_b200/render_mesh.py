@@ -94,7 +94,7 @@ class Renderer:
         if self.reject_behind_camera:
             flags |= _lib.LP_FLAG_REJECT_BEHIND
         cfg = functional.RenderConfig(
-            verts=functional._f32(verts, self.device), faces=functional._faces_i32(faces, self.device),
+            verts=functional._f32(verts, self.device), faces=functional._faces_i32(faces, self.device, verts.shape[0]),
             cameras=cam.contiguous(), proj=self._proj[P], H=int(dims[1]), W=int(dims[0]), flags=flags,
             interp='bilinear',                                           # hard-coded in the reference, render.py:243
             face_uv=functional._f32(uv_face_attr, self.device).reshape(-1, 3, 2),

@@ -61,3 +61,55 @@ def assert_close(a, b, what, rtol=RTOL, atol=ATOL):
     tol = atol + rtol * b.abs()
     bad = err > tol
     assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} elements off, max abs err {float(err.max()):.3e}"
+
+
+U32 = 2.0 ** -24                  # unit roundoff of fp32
+
+
+def accumulation_tolerance(n_terms, rms, atol=ATOL):
+    """Tolerance for ONE texel that is the fp32 sum of ``n_terms`` contributions of root-mean-square magnitude ``rms``
+    added one at a time in an arbitrary order (atomics on the GPU, a loop on the CPU) — the mesh flavour's background
+    texel, which every uncovered pixel of every view feeds with weight 1 ("background-texel leak").
+    Model: the partial sum after k additions is a random walk of size rms * sqrt(k); addition k rounds by at most
+    u * |partial sum|, so the accumulated rounding is itself a random walk with standard deviation
+    u * rms * sqrt(sum_k k) = u * rms * n / sqrt(2).  The bound is six standard deviations plus the pixel atol.  (The
+    worst-case bound (n - 1) * u * sum|x_i| is orders of magnitude looser and would hide real errors.)"""
+    return atol + 6.0 * U32 * rms * n_terms / 2 ** 0.5
+
+
+def assert_texture_grad_close(got, ref, what, background=None, rtol=RTOL, atol=ATOL):
+    """``got`` / ``ref`` (..., C, T, T) texture gradients.  Everything at rtol / atol; ``background`` =
+    ``(n_pixels, rms, ref64)`` relaxes ONLY texel (row T-1, col 0) to the accumulation bound around the fp64
+    sum ``ref64`` (C,), and checks that the fp32 CPU reference obeys the same bound (so the bound is not hiding a bug)."""
+    got = torch.as_tensor(got).detach().cpu().float().reshape(-1, *torch.as_tensor(ref).shape[-3:])
+    ref = torch.as_tensor(ref).detach().cpu().float().reshape(got.shape)
+    if background is not None:
+        n, rms, ref64 = background
+        tol = accumulation_tolerance(n, rms)
+        g_bg, r_bg = got[:, :, -1, 0].double().sum(0), ref[:, :, -1, 0].double().sum(0)
+        ref64 = torch.as_tensor(ref64).double().reshape(-1)
+        assert float((g_bg - ref64).abs().max()) <= tol, \
+            f"{what}: background texel off by {float((g_bg - ref64).abs().max()):.3e} > derived bound {tol:.3e} ({n} terms, rms {rms:.2f})"
+        assert float((r_bg - ref64).abs().max()) <= tol, f"{what}: the fp32 CPU reference itself violates the derived bound"
+        got, ref = got.clone(), ref.clone()
+        got[:, :, -1, 0] = 0
+        ref[:, :, -1, 0] = 0
+    assert_close(got, ref, what, rtol=rtol, atol=atol)
+
+
+def fp64_corner_texel(uv, tex, grad, face_idx):
+    """The gradient of texel (T-1, 0) summed in fp64 (same fp32 inputs, the real ATen grid_sample arithmetic in double),
+    plus the number of uncovered pixels feeding it and the rms of their upstream gradient."""
+    from oracle import kaolin_shim as kal
+    uv, tex, grad, face_idx = (torch.as_tensor(x).detach().cpu() for x in (uv, tex, grad, face_idx))
+    B = uv.shape[0]
+    out = torch.zeros(tex.shape[1], dtype=torch.float64)
+    for i in range(0, B, 8):
+        t64 = tex.detach().double().repeat(min(8, B - i), 1, 1, 1).requires_grad_(True)
+        img = kal.texture_mapping(uv[i:i + 8].double(), t64, "bilinear")          # (b,H,W,C)
+        img.backward(grad[i:i + 8].permute(0, 2, 3, 1).double())
+        out += t64.grad[:, :, -1, 0].sum(0)
+    bg = face_idx < 0
+    n = int(bg.sum())
+    gb = grad.permute(0, 2, 3, 1)[bg]
+    return n, float(torch.sqrt((gb.double() ** 2).mean())) if n else 0.0, out

@@ -1,0 +1,201 @@
+"""GPU parity of the BENCHED configuration (run with -m gpu): the exact call chain ``bench.py`` times —
+``DeviceStep`` through the C ABI with the split pipeline (``lp_render_prepare`` -> ``lp_render_raster`` ->
+``lp_render_shade`` -> ``lp_render_backward``), tile flags, vector REDs and ``LP_FLAG_GRAD_OVERWRITE`` /
+``LP_FLAG_GRAD_INTERLEAVED`` — against the CPU oracle on the same seeded inputs, at BASELINE.json's full sizes
+(configs[1], [2], [3]), plus the depth / barycentric buffers and UVs outside the unit square.
+
+Bars (BASELINE.json north_star): face_idx and the 0/1 mask bit-exact; pixels and gradients rtol 1e-4 / atol 1e-5;
+the one texel that sums tens of thousands of background pixels gets the derived accumulation bound of tests/common.py.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import latent_nerf_test_b200 as lp
+from latent_nerf_test_b200 import _lib
+from oracle import kaolin_shim as kal
+from oracle import renderer_ref
+from tests.common import assert_close, assert_texture_grad_close, fp64_corner_texel, rnd, scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    kal.RASTER_IMPL = "bbox"
+
+
+def _geom(verts, faces, uv):
+    return (verts.to(DEV).float().contiguous(), faces.to(DEV, torch.int32).contiguous(),
+            uv.to(DEV).float().reshape(-1, 3, 2).contiguous())
+
+
+def _oracle_lp_batch(w, verts, faces, uv, tex, grad, views):
+    """latent_paint flavour, one view per call as the reference does; → images, masks, face_idx, summed gradient."""
+    radius, theta, phi = views
+    t = tex.detach().cpu().clone().requires_grad_(True)
+    ref = renderer_ref.LatentPaintRendererRef(dim=(w["W"], w["H"]), interpolation_mode=w["interp"])
+    images, masks, fidx, depth, bary = [], [], [], [], []
+    for i in range(len(theta)):
+        image, mask = ref.render_single_view_texture(verts, faces, uv, t, elev=float(theta[i]), azim=float(phi[i]),
+                                                     radius=float(radius[i]), look_at_height=w["dy"])
+        image.backward(grad[i:i + 1])
+        images.append(image.detach()); masks.append(mask); fidx.append(ref.last["face_idx"])
+        depth.append(kal.LAST["depth"].clone()); bary.append(kal.LAST["bary"].clone())
+    return torch.cat(images), torch.cat(masks), torch.cat(fidx), t.grad[0], torch.cat(depth), torch.cat(bary)
+
+
+@pytest.mark.parametrize("exchange_form", [False, True])
+def test_config2_benched_step_vs_oracle(exchange_form):
+    """configs[1] exactly as bench.py runs it: B = 8, 512 x 512, 3 x 1024^2 texture, split pipeline.  With
+    ``exchange_form`` the backward leaves the gradient interleaved and lp_allreduce_unpack (world 1) finishes it —
+    the form the N > 1 bench uses."""
+    from bench import WORKLOADS, DeviceStep, make_views, workload_cameras
+    w = WORKLOADS["c2"]
+    verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
+    B, C, T = w["B"], w["C"], w["T"]
+    ntex = T * T
+    both = torch.zeros(C * ntex + 4 * ntex, device=DEV)
+    kw = dict(grad_tex=both[:C * ntex].view(C, T, T), accum=both[C * ntex:]) if exchange_form else {}
+    st = DeviceStep(_geom(verts, faces, uv), w, workload_cameras(w, B, 0), 1, torch.device(DEV), **kw)
+    st.run_split()
+    if exchange_form:
+        ptrs = torch.tensor([both.data_ptr()], dtype=torch.int64, device=DEV)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib().lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
+    torch.cuda.synchronize()
+    oi, om, ofi, og, _, _ = _oracle_lp_batch(w, verts, faces, uv, st.tex, st.grad_image.cpu(), make_views(B, 0))
+    assert torch.equal(st.mask.cpu(), om), "0/1 mask (= face_idx > -1) must be bit-exact"
+    assert torch.equal(st.mask.cpu()[:, 0] > 0, ofi >= 0)
+    assert_close(st.image, oi, "image of the benched step")
+    assert_close(st.grad_tex, og, "texture gradient of the benched step (8 views summed)")
+    # tile flags: 1 exactly where the 16 x 16 tile holds a covered pixel
+    cov = (ofi >= 0).reshape(B, w["H"] // 16, 16, w["W"] // 16, 16).any(dim=4).any(dim=2)
+    assert torch.equal(st.tile_any.cpu().bool(), cov)
+    # second run of the same buffers: deterministic visibility, gradient overwritten (not accumulated twice)
+    img1, g1 = st.image.clone(), st.grad_tex.clone()
+    st.run_split()
+    if exchange_form:
+        _lib.check(_lib.lib().lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(st.image, img1)
+    assert_close(st.grad_tex, g1, "gradient of a second step on the same buffers", rtol=1e-5, atol=1e-6)
+
+
+def test_config2_visibility_buffers_vs_oracle():
+    """face_idx, depth and barycentric weights of configs[1] (B = 8 in one call) against the oracle's buffers:
+    same fp32 expression tree in the same order, so all three are compared bit for bit."""
+    from bench import WORKLOADS, DeviceStep, make_views, workload_cameras
+    w = WORKLOADS["c2"]
+    verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
+    B, H, W = w["B"], w["H"], w["W"]
+    st = DeviceStep(_geom(verts, faces, uv), w, workload_cameras(w, B, 0), 1, torch.device(DEV))
+    face_idx = torch.empty(B, H, W, dtype=torch.int32, device=DEV)
+    bary = torch.empty(B, H, W, 3, device=DEV)
+    depth = torch.empty(B, H, W, device=DEV)
+    st.fwd.face_idx, st.fwd.bary, st.fwd.depth = face_idx.data_ptr(), bary.data_ptr(), depth.data_ptr()
+    st.run_split()
+    torch.cuda.synchronize()
+    oi, om, ofi, og, odepth, obary = _oracle_lp_batch(w, verts, faces, uv, st.tex, st.grad_image.cpu(), make_views(B, 0))
+    assert torch.equal(face_idx.cpu().long(), ofi)
+    assert torch.equal(depth.cpu(), odepth), f"depth: max |diff| {float((depth.cpu() - odepth).abs().max()):.3e}"
+    assert torch.equal(bary.cpu(), obary), f"bary: max |diff| {float((bary.cpu() - obary).abs().max()):.3e}"
+    assert_close(st.image, oi, "image (buffers requested)")
+    assert_close(st.grad_tex, og, "texture gradient (buffers requested)")
+
+
+def test_config3_mesh_flavour_B64_vs_oracle():
+    """configs[2]: teddy, 4 x 512^2 latent texture, 64 views at 64 x 64, latent_paint_mesh flavour, through the
+    benched DeviceStep chain.  The image is NOT masked in this flavour, so every uncovered pixel of every view
+    back-propagates into texel (T-1, 0): that texel is compared with the fp64 sum under the derived bound."""
+    from bench import WORKLOADS, DeviceStep, make_views, workload_cameras, LOOK_AT_BODY
+    w = WORKLOADS["c3"]
+    verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
+    B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
+    st = DeviceStep(_geom(verts, faces, uv), w, workload_cameras(w, B, 0), 1, torch.device(DEV))
+    face_idx = torch.empty(B, H, W, dtype=torch.int32, device=DEV)
+    st.fwd.face_idx = face_idx.data_ptr()
+    st.run_split()
+    torch.cuda.synchronize()
+    radius, theta, phi = make_views(B, 0, "mesh")
+    t = st.tex.detach().cpu().clone().requires_grad_(True)
+    ref = renderer_ref.LatentPaintMeshRendererRef(dim=(W, H))
+    routs = ref.render_single_view_texture(verts, faces, uv, t, theta, phi, radius, dims=(W, H), is_body=True)
+    g = st.grad_image.cpu()
+    routs[0].backward(g)
+    ofi = ref.last["face_idx"]
+    assert torch.equal(face_idx.cpu().long(), ofi), "face_idx must be bit-exact"
+    assert torch.equal(st.mask.cpu()[:, 0] > 0, ofi >= 0)
+    for got, want, name in ((st.image, routs[0], "image"), (st.mask, routs[1], "mask"), (st.normals, routs[2], "normals"),
+                            (st.lighting, routs[3], "lighting")):
+        assert_close(got, want, name)
+    n, rms, ref64 = fp64_corner_texel(ref.last["uv"], t, g, ofi)
+    assert n > 10000, "the background texel must be a real accumulation in this test"
+    assert_texture_grad_close(st.grad_tex, t.grad[0], "texture gradient (64 views)", background=(n, rms, ref64))
+
+
+def test_config4_full_size_one_view_vs_oracle():
+    """configs[3] geometry at full size: sphere.obj subdivided five times (1 310 720 faces), 1024 x 1024,
+    3 x 1024^2 texture, one view, through the C ABI chain of the bench (micro-face path)."""
+    from bench import WORKLOADS, DeviceStep, make_views, workload_cameras
+    w = dict(WORKLOADS["c4"], B=1)
+    verts, faces, uv = scene(w["shape"], w["scale"], w["dy"], subdivide=w["subdivide"])
+    assert faces.shape[0] == 1310720
+    H, W = w["H"], w["W"]
+    st = DeviceStep(_geom(verts, faces, uv), w, workload_cameras(w, 1, 3), 1, torch.device(DEV))
+    face_idx = torch.empty(1, H, W, dtype=torch.int32, device=DEV)
+    st.fwd.face_idx = face_idx.data_ptr()
+    st.run_split()
+    torch.cuda.synchronize()
+    oi, om, ofi, og, _, _ = _oracle_lp_batch(w, verts, faces, uv, st.tex, st.grad_image.cpu(), make_views(1, 3))
+    assert torch.equal(face_idx.cpu().long(), ofi)
+    assert torch.equal(st.mask.cpu(), om)
+    assert float(om.mean()) > 0.2
+    assert_close(st.image, oi, "image")
+    assert_close(st.grad_tex, og, "texture gradient")
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_uvs_outside_the_unit_square(mode):
+    """Meshes whose vt lie outside [0,1] (animal / hand / potion.obj in the reference's shapes/): kaolin clamps inside
+    texture_mapping, the pixel stays covered (mask 1) and its gradient goes to the border texel.  Fused and split
+    forward, autograd and C-ABI backward must all agree with the oracle."""
+    from bench import DeviceStep, make_views, cameras_for
+    verts, faces, uv = scene("blub", 0.6, 0.25)
+    uv = uv * 2.0 - 0.5                                          # u, v in [-0.5, 1.5]: a third of the surface is outside
+    C, T, H, W = 4, 64, 96, 80
+    tex = rnd((1, C, T, T), 1, 0.4)
+    g = rnd((1, C, H, W), 2)
+    view = dict(elev=1.0, azim=0.7, radius=1.25, look_at_height=0.25)
+    tc = tex.clone().requires_grad_(True)
+    ref = renderer_ref.LatentPaintRendererRef(dim=(W, H), interpolation_mode=mode)
+    oi, om = ref.render_single_view_texture(verts, faces, uv, tc, **view)
+    oi.backward(g)
+    ouv = ref.last["uv"]
+    assert float((ouv[..., 0] < 0).float().mean()) > 0.01, "the test needs covered pixels with negative u"
+    # fused forward + autograd backward (Python API)
+    tg = tex.to(DEV).requires_grad_(True)
+    r = lp.LatentPaintRenderer(DEV, dim=(W, H), interpolation_mode=mode)
+    r.keep_buffers = True
+    ig, mg = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tg, **view)
+    ig.backward(g.to(DEV))
+    assert torch.equal(mg.cpu(), om)
+    assert_close(ig, oi, f"image, fused ({mode})")
+    assert_close(tg.grad, tc.grad, f"grad_texture, fused ({mode})")
+    assert_close(r.last_buffers["uv"], ouv, "uv returned to the caller (unclamped, 0 where uncovered)")
+    # split forward + C-ABI backward (the benched chain)
+    w = dict(B=1, H=H, W=W, C=C, T=T, interp=mode, flavour="lp", dy=0.25)
+    cams = lp.camera.camera_from_view(torch.tensor(view["elev"]), torch.tensor(view["azim"]), view["radius"], 0.25)
+    st = DeviceStep(_geom(verts, faces, uv), w, cams, 1, torch.device(DEV))
+    st.tex.copy_(tex)
+    st.grad_image.copy_(g)
+    st.run_split()
+    torch.cuda.synchronize()
+    assert torch.equal(st.mask.cpu(), om)
+    assert_close(st.image, oi, f"image, split ({mode})")
+    assert_close(st.grad_tex, tc.grad[0], f"grad_texture, split ({mode})")

@@ -15,7 +15,8 @@ import latent_nerf_test_b200 as lp
 from latent_nerf_test_b200 import _lib, functional
 from oracle import kaolin_shim as kal
 from oracle import renderer_ref
-from tests.common import assert_close, latent_paint_views, load_golden, mesh_views, rnd, scene
+from tests.common import (assert_close, assert_texture_grad_close, fp64_corner_texel, latent_paint_views, load_golden,
+                          mesh_views, rnd, scene)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -88,7 +89,9 @@ def test_golden_mesh_flavour(case):
         assert_close(o, gd[k], k)
     assert np.array_equal((outs[1] > 0).cpu().numpy(), gd["face_idx"][:, None] >= 0)
     outs[0].backward(torch.tensor(gd["grad_image"], device=DEV))
-    assert_close(tex.grad, gd["grad_texture"], "grad_texture", rtol=1e-4, atol=2e-5)
+    # unmasked flavour: texel (T-1, 0) sums every uncovered pixel -> derived accumulation bound around the fp64 sum
+    bg = fp64_corner_texel(r.last_buffers["uv"], tex, gd["grad_image"], gd["face_idx"])
+    assert_texture_grad_close(tex.grad, gd["grad_texture"], "grad_texture", background=bg)
 
 
 # ------------------------------------------------------------------ oracle, seeded random views
@@ -148,7 +151,8 @@ def test_mesh_flavour_vs_oracle_batched():
         assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ref.last["face_idx"])
         for o, ro, k in zip(outs, routs, ("image", "mask", "normals", "lighting")):
             assert_close(o, ro, k)
-        assert_close(tex.grad, t.grad, "grad_texture", rtol=1e-4, atol=1e-4 if is_body else 1e-5)
+        bg = fp64_corner_texel(ref.last["uv"], t, g, ref.last["face_idx"])
+        assert_texture_grad_close(tex.grad, t.grad, "grad_texture", background=bg)
 
 
 def test_device_cameras_and_visibility_with_them():
@@ -339,7 +343,9 @@ def test_host_buffer_step_matches_device_path():
     hs = HostStep(verts, faces, uv, tex.detach(), B, H, W, "bilinear", np.pi / 3)
     image_h, mask_h, grad_h = hs.step(cams, g)
     assert_close(image_h, torch.cat(imgs), "image through host buffers")
-    assert_close(grad_h, tex.grad[0], "grad_texture through host buffers", rtol=1e-4, atol=2e-5)
+    # two different summation orders of the same per-view contributions (views one by one through autograd vs one
+    # batched scatter): each texel sums a handful of fp32 terms, so the pixel tolerance applies unchanged
+    assert_close(grad_h, tex.grad[0], "grad_texture through host buffers")
 
 
 # ------------------------------------------------------------------ kaolin-namespaced operator API
@@ -395,7 +401,8 @@ def test_kaolin_compat_runs_the_reference_glue_on_the_kernels():
     assert torch.equal(rg.last["face_idx"].cpu(), rc.last["face_idx"])
     for a, b, k in zip(og, oc, ("image", "mask", "normals", "lighting")):
         assert_close(a, b, k)
-    assert_close(tg.grad, tc.grad, "grad_texture (mesh flavour)", rtol=1e-4, atol=1e-4)
+    bg = fp64_corner_texel(rc.last["uv"], tc, g, rc.last["face_idx"])
+    assert_texture_grad_close(tg.grad, tc.grad, "grad_texture (mesh flavour)", background=bg)
 
 
 def test_split_forward_equals_fused_forward():
@@ -542,7 +549,9 @@ def test_fused_render_train_composition():
                                         colors.detach().cpu(), view["theta"], view["phi"], view["radius"], dy=0.25)
     for k in ("image", "mask", "background", "foreground"):
         assert tuple(o96[k].shape[-2:]) == (64, 64)
-        assert_close(o96[k], e96[k], k + " (resized)", rtol=1e-4, atol=2e-5)
+        # the bicubic filter has negative lobes (weights in [-0.07, 0.6], |w| summing to <= 1.5625^2): it amplifies
+        # the per-pixel fp32 differences of its 16 inputs by at most that factor
+        assert_close(o96[k], e96[k], k + " (resized)", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
 
 
 def test_fused_adam_matches_torch_adam():
