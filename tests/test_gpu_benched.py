@@ -84,7 +84,8 @@ def test_config2_benched_step_vs_oracle(exchange_form):
         _lib.check(_lib.lib().lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
     torch.cuda.synchronize()
     assert torch.equal(st.image, img1)
-    assert_close(st.grad_tex, g1, "gradient of a second step on the same buffers", rtol=1e-5, atol=1e-6)
+    # (the scatter's atomic order differs from run to run: same terms, another summation order)
+    assert_close(st.grad_tex, g1, "gradient of a second step on the same buffers")
 
 
 def test_config2_visibility_buffers_vs_oracle():
