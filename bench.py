@@ -122,7 +122,7 @@ class DeviceStep:
         self.mask = torch.empty(B, 1, H, W, device=device)
         self.uv = torch.empty(B, H, W, 2, device=device)
         self.grad_tex = torch.zeros(C, T, T, device=device) if grad_tex is None else grad_tex
-        self.tile_any = torch.empty(B, (H + 15) // 16, (W + 15) // 16, dtype=torch.uint8, device=device)
+        self.footprint_any = torch.empty(B, (H + 3) // 4, (W + 7) // 8, dtype=torch.uint8, device=device)
         L = _lib.lib()
         self.ws = torch.empty(int(L.lp_workspace_bytes(B, faces.shape[0], H, W)), dtype=torch.uint8, device=device)
         a = _lib.LpForwardArgs()
@@ -137,7 +137,7 @@ class DeviceStep:
         a.interp = _lib.LP_INTERP_BILINEAR if w["interp"] == "bilinear" else _lib.LP_INTERP_NEAREST
         a.image, a.mask, a.uv = self.image.data_ptr(), self.mask.data_ptr(), self.uv.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
-        a.tile_any = self.tile_any.data_ptr()
+        a.footprint_any = self.footprint_any.data_ptr()
         self.keep = [verts, faces, uv]
         if mesh_flavour:
             V, F = verts.shape[0], faces.shape[0]
@@ -158,7 +158,7 @@ class DeviceStep:
         b.grad_image, b.uv = self.grad_image.data_ptr(), self.uv.data_ptr()
         b.C, b.Th, b.Tw, b.interp = C, T, T, a.interp
         b.grad_texture = self.grad_tex.data_ptr()
-        b.tile_any = self.tile_any.data_ptr()
+        b.footprint_any = self.footprint_any.data_ptr()
         if accum is not None:
             # N > 1, fused exchange: the accumulation buffer lives in symmetric memory next to the planar gradient;
             # the backward leaves the gradient interleaved and lp_allreduce_unpack reduces + unpacks + broadcasts it
@@ -738,6 +738,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the render path has no CPU implementation (use --impl reference)")
     env = Env()
+    for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM)):   # experiments
+        if os.environ.get(name):
+            _lib.check(_lib.lib().lp_set_option(opt, int(os.environ[name])))
     res = measure(args, env, w, full=True)
     strong = None
     if args.workload == "c2" and not args.no_strong and WORKLOADS["c3"]["B"] % env.world == 0:

@@ -121,9 +121,9 @@ typedef struct LpForwardArgs {
     float         *depth;          /* (B,H,W) camera-space z of the visible surface, 0 = none */
     float         *normals;        /* (B,3,H,W) interpolated averaged vertex normals */
     float         *lighting;       /* (B,1,H,W) clamp(SH(normals)·lights, 1e-8, 1) */
-    uint8_t       *tile_any;       /* optional (B, ceil(H/16), ceil(W/16)): 1 where the 16x16 tile holds a covered
-                                      pixel.  With LP_FLAG_MASK_IMAGE the saved uv of the other tiles is then NOT
-                                      written, so the same buffer must be passed to lp_render_backward */
+    uint8_t       *footprint_any;  /* optional (B, ceil(H/4), ceil(W/8)): 1 where the 8 x 4-pixel footprint (the pixels one warp
+                                      rasterizes) holds a covered pixel.  With LP_FLAG_MASK_IMAGE the saved uv of the other
+                                      footprints is then NOT written, so the same buffer must be passed to lp_render_backward */
     /* scratch */
     void          *workspace;
     uint64_t       workspace_bytes;
@@ -151,7 +151,7 @@ typedef struct LpBackwardArgs {
     const float   *bary;           /* (B,H,W,3) */
     int32_t        F, D, features_batched;
     float         *grad_face_features; /* (Bf,F,3,D); ACCUMULATED into */
-    const uint8_t *tile_any;       /* optional, written by the forward call (used with LP_FLAG_MASK_IMAGE) */
+    const uint8_t *footprint_any;       /* optional, written by the forward call (used with LP_FLAG_MASK_IMAGE) */
     /* optional scratch of lp_backward_workspace_bytes(): with it (and C <= 4) the taps are accumulated with
        16-byte vector REDs into a texel-interleaved (Th,Tw,4) buffer and then unpacked into grad_texture —
        a third of the atomic operations of the planar path */
@@ -173,6 +173,12 @@ typedef struct LpTextureMapArgs {
 } LpTextureMapArgs;
 
 int         lp_version(void);
+/* process-wide switches.  LP_OPT_PDL (default 1): chain the kernels of a call with programmatic dependent launch
+ * (each kernel's prologue overlaps its predecessor's tail); 0 = plain stream-ordered launches.
+ * LP_OPT_RASTER_CTAS_PER_SM (default 0 = all the tile kernel's launch bounds allow): resident CTAs per SM of the
+ * persistent tile kernel; fewer leave room for kernels of other streams to run beside it */
+enum { LP_OPT_PDL = 1, LP_OPT_RASTER_CTAS_PER_SM = 2 };
+int         lp_set_option(int option, int value);
 const char *lp_last_error(void);
 const char *lp_error_string(int code);
 
@@ -191,7 +197,7 @@ int lp_render_forward(const LpForwardArgs *args, void *stream);
  * the gradient all-reduce of the current one on another stream:
  *   lp_render_prepare  stage 1 + binning                      (needs verts / cameras, fills the workspace)
  *   lp_render_raster   stage 2-3: visibility, uv, mask, optional buffers  (needs the prepared workspace)
- *   lp_render_shade    stage 4: texture fetch + composition -> image     (needs uv [, mask, tile_any] of the raster call)
+ *   lp_render_shade    stage 4: texture fetch + composition -> image     (needs uv [, mask, footprint_any] of the raster call)
  * All three take the same argument block as lp_render_forward, which runs 1-4 with the fetch fused into the tile kernel. */
 int lp_render_prepare(const LpForwardArgs *args, void *stream);
 int lp_render_raster(const LpForwardArgs *args, void *stream);

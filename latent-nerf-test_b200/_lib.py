@@ -32,10 +32,12 @@ LP_FLAG_GRAD_OVERWRITE = 1 << 5
 LP_FLAG_GRAD_INTERLEAVED = 1 << 6
 LP_FLAG_MICRO_OFF = 1 << 22
 LP_FLAG_MICRO_ON = 1 << 23
+LP_OPT_PDL = 1
+LP_OPT_RASTER_CTAS_PER_SM = 2
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option"]
 
 
 class LpForwardArgs(Structure):
@@ -50,7 +52,7 @@ class LpForwardArgs(Structure):
         ("vf_offsets", c_void_p), ("vf_faces", c_void_p), ("face_normals", c_void_p), ("vertex_normals", c_void_p),
         ("lights", c_void_p),
         ("image", c_void_p), ("mask", c_void_p), ("uv", c_void_p), ("face_idx", c_void_p), ("bary", c_void_p),
-        ("depth", c_void_p), ("normals", c_void_p), ("lighting", c_void_p), ("tile_any", c_void_p),
+        ("depth", c_void_p), ("normals", c_void_p), ("lighting", c_void_p), ("footprint_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
         ("under_image", c_void_p), ("under_mask", c_void_p), ("composed", c_void_p),
     ]
@@ -64,7 +66,7 @@ class LpBackwardArgs(Structure):
         ("grad_texture", c_void_p), ("grad_texture_batch_stride", ctypes.c_int64),
         ("face_idx", c_void_p), ("bary", c_void_p),
         ("F", c_int32), ("D", c_int32), ("features_batched", c_int32),
-        ("grad_face_features", c_void_p), ("tile_any", c_void_p),
+        ("grad_face_features", c_void_p), ("footprint_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
         ("under_mask", c_void_p),
     ]
@@ -154,6 +156,8 @@ def lib() -> ctypes.CDLL:
     L.lp_last_launch_count.restype = c_int32
     L.lp_timing_enable.restype = c_int32
     L.lp_timing_enable.argtypes = [c_int32]
+    L.lp_set_option.restype = c_int32
+    L.lp_set_option.argtypes = [c_int32, c_int32]
     L.lp_timing_collect.restype = c_int32
     L.lp_timing_collect.argtypes = [c_int32, POINTER(c_char_p), POINTER(c_float), POINTER(c_int32)]
     _lib = L

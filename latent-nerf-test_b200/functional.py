@@ -193,13 +193,13 @@ class _RenderTexture(torch.autograd.Function):
                 a.lights, a.normals, a.lighting = _ptr(cfg.lights), _ptr(normals), _ptr(lighting)
                 keep += [off, vf, fn, vn]
             a.image, a.mask, a.uv = _ptr(image), _ptr(mask), _ptr(uv)
-            tile_any = torch.empty((B, (H + 15) // 16, (W + 15) // 16), dtype=torch.uint8, device=device)
-            a.tile_any = _ptr(tile_any)
+            footprint_any = torch.empty((B, (H + 3) // 4, (W + 7) // 8), dtype=torch.uint8, device=device)
+            a.footprint_any = _ptr(footprint_any)
             _lib.check(_lib.lib().lp_render_forward(ctypes.byref(a), _stream(device)))
             launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
         ctx.cfg = cfg
         ctx.tex_shape = tuple(texture.shape)
-        ctx.save_for_backward(uv, tile_any)
+        ctx.save_for_backward(uv, footprint_any)
         # the saved uv carries the kernels' own conventions (NaN on uncovered pixels of the masked flavour, tiles
         # without coverage not written at all); what the caller sees is kaolin's: 0 where nothing is covered
         uv_out = torch.where(face_idx[..., None] >= 0, uv, torch.zeros_like(uv)) if cfg.want_buffers else uv
@@ -209,7 +209,7 @@ class _RenderTexture(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_image, *unused):
-        uv, tile_any = ctx.saved_tensors
+        uv, footprint_any = ctx.saved_tensors
         cfg = ctx.cfg
         device = uv.device
         _, C, Th, Tw = ctx.tex_shape
@@ -227,7 +227,7 @@ class _RenderTexture(torch.autograd.Function):
         b.grad_image, b.uv = _ptr(g), _ptr(uv)
         b.C, b.Th, b.Tw, b.interp = C, Th, Tw, _INTERP[cfg.interp]
         b.grad_texture = _ptr(grad_tex)
-        b.tile_any = _ptr(tile_any)
+        b.footprint_any = _ptr(footprint_any)
         with torch.cuda.device(device):
             _lib.check(_lib.lib().lp_render_backward(ctypes.byref(b), _stream(device)))
             launch_counter["kernels"] += _lib.lib().lp_last_launch_count()
@@ -328,13 +328,13 @@ class _RenderComposed(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_composed, g_mask, g_back, g_fg):
-        face_idx, bary, mask, uv, tile_any = ctx.saved_tensors
+        face_idx, bary, mask, uv, footprint_any = ctx.saved_tensors
         device = face_idx.device
         grad_tex = grad_ff = None
         # texture: d composed / d foreground = mask, and the texture scatter only sees covered pixels (mask = 1)
         g_t = g_composed if g_fg is None else (g_fg if g_composed is None else g_composed + g_fg)
         if g_t is not None and ctx.needs_input_grad[0]:
-            ctx.tex_ctx.saved_tensors = (uv, tile_any)
+            ctx.tex_ctx.saved_tensors = (uv, footprint_any)
             grad_tex, _ = _RenderTexture.backward(ctx.tex_ctx, g_t)
         if (g_composed is not None or g_back is not None) and ctx.needs_input_grad[1]:
             cfg = ctx.feat_cfg

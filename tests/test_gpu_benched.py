@@ -74,9 +74,9 @@ def test_config2_benched_step_vs_oracle(exchange_form):
     assert torch.equal(st.mask.cpu()[:, 0] > 0, ofi >= 0)
     assert_close(st.image, oi, "image of the benched step")
     assert_close(st.grad_tex, og, "texture gradient of the benched step (8 views summed)")
-    # tile flags: 1 exactly where the 16 x 16 tile holds a covered pixel
-    cov = (ofi >= 0).reshape(B, w["H"] // 16, 16, w["W"] // 16, 16).any(dim=4).any(dim=2)
-    assert torch.equal(st.tile_any.cpu().bool(), cov)
+    # coverage flags: 1 exactly where the 8 x 4-pixel footprint holds a covered pixel
+    cov = (ofi >= 0).reshape(B, w["H"] // 4, 4, w["W"] // 8, 8).any(dim=4).any(dim=2)
+    assert torch.equal(st.footprint_any.cpu().bool(), cov)
     # second run of the same buffers: deterministic visibility, gradient overwritten (not accumulated twice)
     img1, g1 = st.image.clone(), st.grad_tex.clone()
     st.run_split()
@@ -200,3 +200,46 @@ def test_uvs_outside_the_unit_square(mode):
     assert torch.equal(st.mask.cpu(), om)
     assert_close(st.image, oi, f"image, split ({mode})")
     assert_close(st.grad_tex, tc.grad[0], f"grad_texture, split ({mode})")
+
+
+@pytest.mark.parametrize("pdl", [1, 0])
+def test_bin_overflow_cascade_and_rerun(pdl):
+    """Fixed-capacity cells: with the micro-face path switched off, blub's 14 208 faces at 64 x 64 put thousands of
+    faces into single cells, so insertions cascade through the parents up to the root list.  Visibility must not
+    care (bit-exact), with and without programmatic dependent launch, and the prepared bins can be rasterized twice."""
+    from bench import DeviceStep
+    verts, faces, uv = scene("blub", 0.6, 0.25)
+    H = W = 64
+    w = dict(B=2, H=H, W=W, C=4, T=128, interp="bilinear", flavour="lp", dy=0.25)
+    cams = torch.cat([lp.camera.camera_from_view(torch.tensor(e), torch.tensor(a), r, 0.25)
+                      for e, a, r in ((1.0, 0.7, 1.25), (2.0, 4.0, 1.05))])
+    L = _lib.lib()
+    _lib.check(L.lp_set_option(_lib.LP_OPT_PDL, pdl))
+    try:
+        for micro_flag in (_lib.LP_FLAG_MICRO_OFF, _lib.LP_FLAG_MICRO_ON, 0):
+            st = DeviceStep(_geom(verts, faces, uv), w, cams, 1, torch.device(DEV))
+            st.fwd.flags |= micro_flag
+            face_idx = torch.empty(2, H, W, dtype=torch.int32, device=DEV)
+            st.fwd.face_idx = face_idx.data_ptr()
+            st.run_split()
+            torch.cuda.synchronize()
+            ofi = []
+            t = st.tex.detach().cpu().clone().requires_grad_(True)
+            ref = renderer_ref.LatentPaintRendererRef(dim=(W, H), interpolation_mode="bilinear")
+            imgs = []
+            for i, (e, a, r) in enumerate(((1.0, 0.7, 1.25), (2.0, 4.0, 1.05))):
+                img, _ = ref.render_single_view_texture(verts, faces, uv, t, elev=e, azim=a, radius=r, look_at_height=0.25)
+                img.backward(st.grad_image.cpu()[i:i + 1])
+                imgs.append(img.detach()); ofi.append(ref.last["face_idx"])
+            assert torch.equal(face_idx.cpu().long(), torch.cat(ofi)), f"micro flag {micro_flag:#x}"
+            assert_close(st.image, torch.cat(imgs), "image")
+            assert_close(st.grad_tex, t.grad[0], "texture gradient")
+            # rasterize the same prepared bins again (the tile kernel rewinds its own ticket counter)
+            first = face_idx.clone()
+            face_idx.fill_(-5)
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(L.lp_render_raster(ctypes.byref(st.fwd), stream))
+            torch.cuda.synchronize()
+            assert torch.equal(face_idx, first)
+    finally:
+        _lib.check(L.lp_set_option(_lib.LP_OPT_PDL, 1))

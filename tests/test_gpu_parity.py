@@ -312,7 +312,7 @@ def test_c_abi_error_codes_on_device():
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_UNSUPPORTED
     a.interp = 0
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_OK
-    assert L.lp_last_launch_count() == 4        # setup, scan, fill, tile kernel
+    assert L.lp_last_launch_count() == 4        # setup + binning, large-face binning, footprint classification, footprint kernel
     torch.cuda.synchronize()
     assert float(mask.sum()) > 0
     r = lp.LatentPaintRenderer(DEV, dim=(32, 32), interpolation_mode="bicubic")
@@ -429,8 +429,8 @@ def test_split_forward_equals_fused_forward():
         for fn in (L.lp_render_prepare, L.lp_render_raster, L.lp_render_shade):
             _lib.check(fn(ctypes.byref(b_.fwd), stream))
         torch.cuda.synchronize()
-        assert torch.equal(a.image, b_.image) and torch.equal(a.mask, b_.mask) and torch.equal(a.tile_any, b_.tile_any)
-        live = a.tile_any.bool().repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :w["H"], :w["W"]]
+        assert torch.equal(a.image, b_.image) and torch.equal(a.mask, b_.mask) and torch.equal(a.footprint_any, b_.footprint_any)
+        live = a.footprint_any.bool().repeat_interleave(4, 1).repeat_interleave(8, 2)[:, :w["H"], :w["W"]]
         ua, ub = a.uv[live], b_.uv[live]                        # uncovered pixels of live tiles carry the NaN marker
         assert torch.equal(torch.isnan(ua), torch.isnan(ub)) and torch.equal(torch.nan_to_num(ua), torch.nan_to_num(ub))
         assert float(a.mask.sum()) > 0
