@@ -110,7 +110,7 @@ class DeviceStep:
     ``w['flavour']``: 'lp' = latent_paint Renderer (masked image, fov pi/3), 'mesh' = latent_paint_mesh Renderer
     (unmasked image, float mask, normals + SH lighting outputs, nz == 0 culling, body camera)."""
 
-    def __init__(self, geom, w, cams, seed, device, grad_tex=None, accum=None):
+    def __init__(self, geom, w, cams, seed, device, grad_tex=None, accum=None, grad_layout="planar"):
         verts, faces, uv = geom
         B, H, W, C, T = w["B"], w["H"], w["W"], w["C"], w["T"]
         mesh_flavour = w.get("flavour", "lp") == "mesh"
@@ -134,6 +134,11 @@ class DeviceStep:
         a.flags = (_lib.LP_FLAG_CULL_NZ_ZERO if mesh_flavour else _lib.LP_FLAG_MASK_IMAGE) | _lib.LP_FLAG_REJECT_BEHIND
         a.face_uv, a.texture = uv.data_ptr(), self.tex.data_ptr()
         a.C, a.Th, a.Tw = C, T, T
+        # the texture once more, texel-interleaved, for the 16-byte taps of lp_render_shade (repacked by repack()
+        # whenever the texture changes; in a training loop the optimiser step is followed by one repack)
+        self.tex_rgba = torch.empty(T * T, 4, device=device) if C <= 4 and os.environ.get("LP_TEX_RGBA", "1") == "1" else None
+        if self.tex_rgba is not None:
+            a.texture_rgba = self.tex_rgba.data_ptr()
         a.interp = _lib.LP_INTERP_BILINEAR if w["interp"] == "bilinear" else _lib.LP_INTERP_NEAREST
         a.image, a.mask, a.uv = self.image.data_ptr(), self.mask.data_ptr(), self.uv.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
@@ -170,13 +175,34 @@ class DeviceStep:
             if self.accum.numel() and os.environ.get("LP_BWD_VEC", "1") == "1":
                 b.workspace, b.workspace_bytes = self.accum.data_ptr(), self.accum.numel()
                 b.flags |= _lib.LP_FLAG_GRAD_OVERWRITE
+                if grad_layout == "interleaved":
+                    # the gradient stays texel-interleaved (T,T,4) in the accumulation buffer: the layout the fused
+                    # optimiser (lp_adam_step with accum) and lp_allreduce_unpack consume; no unpack pass
+                    b.flags |= _lib.LP_FLAG_GRAD_INTERLEAVED
             else:
                 self.accum = self.accum[:0]
+        self.interleaved = bool(b.flags & _lib.LP_FLAG_GRAD_INTERLEAVED)
         if os.environ.get("LP_DEBUG_BWD_STOP"):
             b.flags |= 1 << int(os.environ["LP_DEBUG_BWD_STOP"])
         self.fwd, self.bwd = a, b
         self.launches = 0
         self.launches_prepare = 0
+        self.repack()
+
+    def repack(self):
+        """(Re)build the texel-interleaved copy of the texture after ``self.tex`` changed."""
+        if self.tex_rgba is not None:
+            C, T = self.tex.shape[1], self.tex.shape[-1]
+            with torch.cuda.device(self.device):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                _lib.check(_lib.lib().lp_pack_texture(self.tex.data_ptr(), C, T, T, self.tex_rgba.data_ptr(), stream))
+
+    def gradient(self):
+        """The texture gradient of the last step as a planar (C,T,T) tensor, whichever layout the step left it in."""
+        if self.interleaved:
+            C, T = self.tex.shape[1], self.tex.shape[-1]
+            return self.accum.view(torch.float32).view(T, T, 4)[:, :, :C].permute(2, 0, 1).contiguous()
+        return self.grad_tex
 
     def prepare(self, stream, with_raster):
         """The texture-independent stages of this set's views on `stream` (a raw cudaStream_t handle):
@@ -238,6 +264,7 @@ class HostStep:
         w = dict(B=B, H=H, W=W, C=C, T=T, interp=interp, flavour=flavour)
         self.dev = DeviceStep(geom, w, torch.zeros(B, 4, 3), 0, self.device)
         self.dev.tex.copy_(texture.reshape(1, C, T, T))
+        self.dev.repack()
         self.h_cams = torch.empty(B, 4, 3).pin_memory()
         self.h_grad = torch.empty(B, C, H, W).pin_memory()
         self.h_image = torch.empty(B, C, H, W).pin_memory()
@@ -448,7 +475,8 @@ def measure(args, env, w, full):
     for s in range(n_sets):
         gt = symm_bufs[s].view((C, T, T)) if symm_bufs else None
         acc = symm_bufs[s].accum if symm_bufs and symm_bufs[s].fused else None
-        sets.append(DeviceStep(geom, w, workload_cameras(w, B, 1000 * rank + s), 10 * s + 1, device, grad_tex=gt, accum=acc))
+        sets.append(DeviceStep(geom, w, workload_cameras(w, B, 1000 * rank + s), 10 * s + 1, device, grad_tex=gt, accum=acc,
+                               grad_layout=args.grad_layout))
     set_bytes = sum(t.numel() * t.element_size() for t in (sets[0].tex, sets[0].grad_image, sets[0].image, sets[0].mask,
                                                            sets[0].uv, sets[0].grad_tex))
 
@@ -725,6 +753,10 @@ def main():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
                     help="texture-gradient exchange at N > 1: the library's own NVLink kernels over symmetric memory "
                          "(multimem = NVSwitch in-switch reduction, p2p = two-shot peer loads) or NCCL")
+    ap.add_argument("--grad-layout", default="interleaved", choices=["interleaved", "planar"],
+                    help="what a step leaves behind: the texture gradient texel-interleaved (T,T,4) — the layout the fused "
+                         "optimiser (lp_adam_step) and the exchange (lp_allreduce_unpack) consume — or the reference's planar "
+                         "(C,T,T), which costs one more pass (k_unpack_grad)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[2] strong-scaling measurement of the default run")
     ap.add_argument("--cpu-views", type=int, default=160, help="views timed for cpu_baseline, about 10-30 s of CPU work (0 = skip)")
@@ -738,7 +770,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the render path has no CPU implementation (use --impl reference)")
     env = Env()
-    for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM)):   # experiments
+    # The persistent footprint kernel needs only two resident CTAs per SM (config 2: 41 us with two, 39 us with four);
+    # the pipelined forms leave the rest of each SM to the kernels of the other streams (measured: 73.9 us per step
+    # with two, 85.8 with three, 86.8 with four).  LP_RASTER_CTAS / LP_PDL override (experiments).
+    if args.pipeline != "off":
+        _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_RASTER_CTAS_PER_SM, 2))
+    for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM)):
         if os.environ.get(name):
             _lib.check(_lib.lib().lp_set_option(opt, int(os.environ[name])))
     res = measure(args, env, w, full=True)
@@ -758,7 +795,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms"] / args.steps, "higher_is_better": True,
                 "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["label"], "views_per_gpu_per_step": res["B"], "cuda_graph": res["cuda_graph"],
-                           "pipeline": res["pipeline"], "l2": res["l2"],
+                           "pipeline": res["pipeline"], "l2": res["l2"], "gradient_layout": args.grad_layout,
                            "parallelism": f"views sharded over {world} GPU(s)" + (f", all-reduce of the texture gradient each step ({res['allreduce_mode']})" if world > 1 else "")},
                 "gpu_launches": res["launches_per_step"] * args.steps, "launches_per_step": res["launches_per_step"],
                 "clocks": res["clocks"], "roofline": res["roofline"], "e2e": res["e2e"], "cpu_baseline": res["cpu"],

@@ -134,6 +134,9 @@ typedef struct LpForwardArgs {
     const float   *under_image;    /* (B,D,H,W) */
     const float   *under_mask;     /* (B,1,H,W) */
     float         *composed;       /* out (B,D,H,W) */
+    /* optional: the texture once more as (Th,Tw,4) texel-interleaved float4 (lp_pack_texture; C <= 4).  lp_render_shade
+       then fetches a tap with one 16-byte load instead of C loads Th*Tw apart; results are the same bits */
+    const void    *texture_rgba;
 } LpForwardArgs;
 
 typedef struct LpBackwardArgs {
@@ -205,6 +208,9 @@ int lp_render_shade(const LpForwardArgs *args, void *stream);
 int lp_render_raster_shade(const LpForwardArgs *args, void *stream);   /* raster + shade in the one fused tile kernel */
 int lp_render_backward(const LpBackwardArgs *args, void *stream);
 int lp_texture_map_forward(const LpTextureMapArgs *args, void *stream);
+/* planar (C,Th,Tw) texture -> (Th,Tw,4) texel-interleaved float4 for LpForwardArgs.texture_rgba (16 * Th * Tw bytes);
+ * repack whenever the texture changes (after the optimiser step) */
+int lp_pack_texture(const float *texture, int32_t C, int32_t Th, int32_t Tw, void *texture_rgba, void *stream);
 
 /* vertex → incident (corner-major, face-ascending) CSR: offsets (V+1), entries (3F) hold face ids.
  * face_normals (B,F,3) → vertex_normals (B,V,3) = mean of incident unit face normals, not re-normalised */

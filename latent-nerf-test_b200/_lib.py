@@ -37,7 +37,7 @@ LP_OPT_RASTER_CTAS_PER_SM = 2
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture"]
 
 
 class LpForwardArgs(Structure):
@@ -55,6 +55,7 @@ class LpForwardArgs(Structure):
         ("depth", c_void_p), ("normals", c_void_p), ("lighting", c_void_p), ("footprint_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
         ("under_image", c_void_p), ("under_mask", c_void_p), ("composed", c_void_p),
+        ("texture_rgba", c_void_p),
     ]
 
 
@@ -156,6 +157,8 @@ def lib() -> ctypes.CDLL:
     L.lp_last_launch_count.restype = c_int32
     L.lp_timing_enable.restype = c_int32
     L.lp_timing_enable.argtypes = [c_int32]
+    L.lp_pack_texture.restype = c_int32
+    L.lp_pack_texture.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     L.lp_set_option.restype = c_int32
     L.lp_set_option.argtypes = [c_int32, c_int32]
     L.lp_timing_collect.restype = c_int32

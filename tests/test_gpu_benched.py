@@ -50,7 +50,7 @@ def _oracle_lp_batch(w, verts, faces, uv, tex, grad, views):
     return torch.cat(images), torch.cat(masks), torch.cat(fidx), t.grad[0], torch.cat(depth), torch.cat(bary)
 
 
-@pytest.mark.parametrize("exchange_form", [False, True])
+@pytest.mark.parametrize("exchange_form", [False, True, "interleaved"])
 def test_config2_benched_step_vs_oracle(exchange_form):
     """configs[1] exactly as bench.py runs it: B = 8, 512 x 512, 3 x 1024^2 texture, split pipeline.  With
     ``exchange_form`` the backward leaves the gradient interleaved and lp_allreduce_unpack (world 1) finishes it —
@@ -61,10 +61,12 @@ def test_config2_benched_step_vs_oracle(exchange_form):
     B, C, T = w["B"], w["C"], w["T"]
     ntex = T * T
     both = torch.zeros(C * ntex + 4 * ntex, device=DEV)
-    kw = dict(grad_tex=both[:C * ntex].view(C, T, T), accum=both[C * ntex:]) if exchange_form else {}
+    kw = dict(grad_tex=both[:C * ntex].view(C, T, T), accum=both[C * ntex:]) if exchange_form is True else {}
+    if exchange_form == "interleaved":          # bench.py's default at N = 1: the gradient stays (T,T,4) for the fused optimiser
+        kw = dict(grad_layout="interleaved")
     st = DeviceStep(_geom(verts, faces, uv), w, workload_cameras(w, B, 0), 1, torch.device(DEV), **kw)
     st.run_split()
-    if exchange_form:
+    if exchange_form is True:
         ptrs = torch.tensor([both.data_ptr()], dtype=torch.int64, device=DEV)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(_lib.lib().lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
@@ -73,19 +75,32 @@ def test_config2_benched_step_vs_oracle(exchange_form):
     assert torch.equal(st.mask.cpu(), om), "0/1 mask (= face_idx > -1) must be bit-exact"
     assert torch.equal(st.mask.cpu()[:, 0] > 0, ofi >= 0)
     assert_close(st.image, oi, "image of the benched step")
-    assert_close(st.grad_tex, og, "texture gradient of the benched step (8 views summed)")
+    assert_close(st.gradient(), og, "texture gradient of the benched step (8 views summed)")
     # coverage flags: 1 exactly where the 8 x 4-pixel footprint holds a covered pixel
     cov = (ofi >= 0).reshape(B, w["H"] // 4, 4, w["W"] // 8, 8).any(dim=4).any(dim=2)
     assert torch.equal(st.footprint_any.cpu().bool(), cov)
     # second run of the same buffers: deterministic visibility, gradient overwritten (not accumulated twice)
-    img1, g1 = st.image.clone(), st.grad_tex.clone()
+    img1, g1 = st.image.clone(), st.gradient().clone()
     st.run_split()
-    if exchange_form:
+    if exchange_form is True:
         _lib.check(_lib.lib().lp_allreduce_unpack(None, ctypes.c_void_p(ptrs.data_ptr()), 4 * C * ntex, 0, ntex, C, 0, 1, stream))
     torch.cuda.synchronize()
     assert torch.equal(st.image, img1)
     # (the scatter's atomic order differs from run to run: same terms, another summation order)
-    assert_close(st.grad_tex, g1, "gradient of a second step on the same buffers")
+    assert_close(st.gradient(), g1, "gradient of a second step on the same buffers")
+    if exchange_form == "interleaved":
+        # ... and the fused optimiser consumes exactly that buffer: one Adam step from it equals torch's on the oracle gradient
+        p_gpu = st.tex.clone()
+        opt = lp.optim.FusedAdam([p_gpu], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+        opt.step_from_accum(p_gpu, st.accum.view(torch.float32).view(-1, 4))
+        p_ref = torch.nn.Parameter(st.tex.detach().cpu().clone())
+        p_ref.grad = og[None].clone()
+        torch.optim.Adam([p_ref], lr=0.01, betas=(0.9, 0.99), eps=1e-15).step()
+        moved = (p_ref.detach() - st.tex.cpu()).abs() > 1e-3           # texels that received gradient
+        assert int(moved.sum()) > 100000
+        # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the gradient is not within rounding of zero
+        solid = og[None].abs() > 1e-4
+        assert_close(p_gpu.cpu()[solid], p_ref.detach()[solid], "texture after one fused Adam step from the interleaved gradient", rtol=1e-5, atol=1e-6)
 
 
 def test_config2_visibility_buffers_vs_oracle():
