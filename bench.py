@@ -775,7 +775,8 @@ def main():
     # with two, 85.8 with three, 86.8 with four).  LP_RASTER_CTAS / LP_PDL override (experiments).
     if args.pipeline != "off":
         _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_RASTER_CTAS_PER_SM, 2))
-    for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM)):
+    for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM),
+                      ("LP_EXCHANGE_CTAS", _lib.LP_OPT_EXCHANGE_CTAS)):
         if os.environ.get(name):
             _lib.check(_lib.lib().lp_set_option(opt, int(os.environ[name])))
     res = measure(args, env, w, full=True)

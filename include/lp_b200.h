@@ -180,7 +180,7 @@ int         lp_version(void);
  * (each kernel's prologue overlaps its predecessor's tail); 0 = plain stream-ordered launches.
  * LP_OPT_RASTER_CTAS_PER_SM (default 0 = all the tile kernel's launch bounds allow): resident CTAs per SM of the
  * persistent tile kernel; fewer leave room for kernels of other streams to run beside it */
-enum { LP_OPT_PDL = 1, LP_OPT_RASTER_CTAS_PER_SM = 2 };
+enum { LP_OPT_PDL = 1, LP_OPT_RASTER_CTAS_PER_SM = 2, LP_OPT_EXCHANGE_CTAS = 3 /* CTAs of lp_exchange_step, 0 = one per SM */ };
 int         lp_set_option(int option, int value);
 const char *lp_last_error(void);
 const char *lp_error_string(int code);
@@ -263,6 +263,29 @@ int lp_adam_step(const LpAdamArgs *args, void *stream);
  * bit-identical sums.  ntex must be a multiple of 4 * world.  Barriers before and after are the caller's, as above. */
 int lp_allreduce_unpack(void *multicast_base, void *const *buffer_ptrs_dev, uint64_t accum_offset, uint64_t grad_offset,
                         int64_t ntex, int32_t C, int32_t rank, int32_t world, void *stream);
+
+/* The exchange as ONE launch, handshakes included: every rank's symmetric allocation also holds LP_EXCHANGE_FLAG_BYTES of
+ * flag words at flags_offset (zeroed once by the caller).  Inside the kernel rank r tells every peer that its backward is
+ * complete, waits for theirs, reduces + unpacks + broadcasts slice r as lp_allreduce_unpack does, and leaves only when every
+ * peer's broadcast has landed — no host-enqueued barrier before, between or after.  Replayable from CUDA graphs (the epoch
+ * lives in the flag block).  With adam != 0 the broadcast is the UPDATED PARAMETER slice instead of the gradient: rank r
+ * owns slice r of the optimiser state (exp_avg / exp_avg_sq: local, planar (C, ntex / world)), applies torch's Adam step
+ * to slice r of the planar (C, ntex) parameters at param_offset and stores it to every rank (reduce slice -> Adam on the
+ * slice -> broadcast parameters; src/latent_paint_mesh/training/trainer.py:326-328 + :407 sharded over the ranks). */
+#define LP_EXCHANGE_FLAG_BYTES 8192
+typedef struct LpExchangeArgs {
+    void        *multicast_base;   /* multicast mapping of the allocation, or NULL: peer loads / stores */
+    void *const *buffer_ptrs_dev;  /* device array of `world` allocation base pointers */
+    uint64_t     accum_offset, grad_offset, flags_offset;   /* bytes from the allocation base */
+    int64_t      ntex;             /* texels, a multiple of 4 * world */
+    int32_t      C, rank, world;
+    int32_t      adam;             /* 0: broadcast the summed gradient to grad_offset; 1: optimiser epilogue */
+    uint64_t     param_offset;     /* adam: planar (C, ntex) parameters in the symmetric allocation */
+    float       *exp_avg, *exp_avg_sq;   /* adam: this rank's slices, planar (C, ntex / world) */
+    float        lr, beta1, beta2, eps;
+    int32_t      step;             /* adam: 1-based step count after this update */
+} LpExchangeArgs;
+int lp_exchange_step(const LpExchangeArgs *args, void *stream);
 
 /* Instrumentation (bench.py's roofline leg): while enabled, every kernel launch of this library is
  * bracketed by CUDA events on its stream.  lp_timing_collect waits for them, sums the elapsed

@@ -34,10 +34,11 @@ LP_FLAG_MICRO_OFF = 1 << 22
 LP_FLAG_MICRO_ON = 1 << 23
 LP_OPT_PDL = 1
 LP_OPT_RASTER_CTAS_PER_SM = 2
+LP_OPT_EXCHANGE_CTAS = 3
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step"]
 
 
 class LpForwardArgs(Structure):
@@ -79,6 +80,19 @@ class LpAdamArgs(Structure):
         ("ntex", ctypes.c_int64), ("C", c_int32), ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
         ("step", c_int32),
     ]
+
+
+class LpExchangeArgs(Structure):
+    _fields_ = [
+        ("multicast_base", c_void_p), ("buffer_ptrs_dev", c_void_p),
+        ("accum_offset", c_uint64), ("grad_offset", c_uint64), ("flags_offset", c_uint64),
+        ("ntex", ctypes.c_int64), ("C", c_int32), ("rank", c_int32), ("world", c_int32), ("adam", c_int32),
+        ("param_offset", c_uint64), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+        ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("step", c_int32),
+    ]
+
+
+LP_EXCHANGE_FLAG_BYTES = 8192
 
 
 class LpTextureMapArgs(Structure):
@@ -159,6 +173,8 @@ def lib() -> ctypes.CDLL:
     L.lp_timing_enable.argtypes = [c_int32]
     L.lp_pack_texture.restype = c_int32
     L.lp_pack_texture.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    L.lp_exchange_step.restype = c_int32
+    L.lp_exchange_step.argtypes = [POINTER(LpExchangeArgs), c_void_p]
     L.lp_set_option.restype = c_int32
     L.lp_set_option.argtypes = [c_int32, c_int32]
     L.lp_timing_collect.restype = c_int32

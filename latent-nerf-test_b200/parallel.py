@@ -75,7 +75,8 @@ class SymmetricGradientBuffer:
     rank owns an equally sized, 16-byte aligned slice.
     """
 
-    def __init__(self, numel: int, device, group=None, interleaved_texels: int = 0, channels: int = 0):
+    def __init__(self, numel: int, device, group=None, interleaved_texels: int = 0, channels: int = 0,
+                 with_params: bool = False):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm
@@ -95,15 +96,24 @@ class SymmetricGradientBuffer:
         self.fused = bool(self.texels) and self.texels % quantum == 0 and 0 < self.channels <= 4 \
             and numel == self.channels * self.texels
         self.accum_floats = 4 * self.texels if self.fused else 0
-        self.flat_all = symm.empty(self.padded + self.accum_floats, dtype=torch.float32, device=device)
+        # layout of the allocation (floats): planar gradient | accumulation buffer | [planar parameters] | flag block
+        self.param_floats = self.padded if (with_params and self.fused) else 0
+        flag_floats = _lib.LP_EXCHANGE_FLAG_BYTES // 4
+        self.flat_all = symm.empty(self.padded + self.accum_floats + self.param_floats + flag_floats, dtype=torch.float32, device=device)
         self.flat_all.zero_()
         self.flat = self.flat_all[:self.padded]
-        self.accum = self.flat_all[self.padded:] if self.fused else None      # (texels, 4) interleaved
+        self.accum = self.flat_all[self.padded:self.padded + self.accum_floats] if self.fused else None      # (texels, 4) interleaved
         self.accum_offset = 4 * self.padded                                   # bytes from the allocation's base
+        self.param_offset = 4 * (self.padded + self.accum_floats)
+        self.params = self.flat_all[self.padded + self.accum_floats:self.padded + self.accum_floats + self.param_floats] \
+            if self.param_floats else None                                    # planar (C, texels): the texture itself
+        self.flags_offset = 4 * (self.padded + self.accum_floats + self.param_floats)
+        self.adam_state = None
         self.handle = symm.rendezvous(self.flat_all, self.group.group_name)
         self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         self.mode = "multimem" if self.multicast_ptr else "p2p"
         self.use_fused = self.fused          # callers may switch back to unpack + all-reduce on the planar gradient
+        self.one_launch = True               # fused form: handshakes inside the kernel (False: barrier, kernel, barrier)
 
     def view(self, shape):
         n = 1
@@ -111,10 +121,40 @@ class SymmetricGradientBuffer:
             n *= s
         return self.flat[:n].view(shape)
 
+    def exchange_step(self, adam=None):
+        """The exchange as ONE kernel launch (``lp_exchange_step``): the handshakes between the ranks happen inside the
+        kernel through the flag block of this allocation, no host-enqueued barrier.  Needs the fused layout.
+        ``adam = dict(lr, betas, eps)`` switches on the sharded optimiser epilogue: every rank updates its slice of
+        ``self.params`` (allocate with ``with_params=True``) and broadcasts it; the optimiser state is sharded."""
+        if not self.fused:
+            raise RuntimeError("exchange_step needs the interleaved accumulation buffer in the allocation")
+        L, c = self._lib.lib(), self._ctypes
+        a = self._lib.LpExchangeArgs()
+        a.multicast_base = c.c_void_p(self.multicast_ptr) if self.mode == "multimem" else None
+        a.buffer_ptrs_dev = c.c_void_p(self.handle.buffer_ptrs_dev)
+        a.accum_offset, a.grad_offset, a.flags_offset = self.accum_offset, 0, self.flags_offset
+        a.ntex, a.C, a.rank, a.world = self.texels, self.channels, self.rank, self.world
+        if adam is not None:
+            if self.params is None:
+                raise RuntimeError("the optimiser epilogue needs with_params=True")
+            if self.adam_state is None:
+                n = self.channels * self.texels // self.world
+                self.adam_state = {"step": 0, "exp_avg": torch.zeros(n, device=self.flat.device),
+                                   "exp_avg_sq": torch.zeros(n, device=self.flat.device)}
+            st = self.adam_state
+            st["step"] += 1
+            a.adam, a.param_offset = 1, self.param_offset
+            a.exp_avg, a.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            a.lr, (a.beta1, a.beta2), a.eps, a.step = adam["lr"], adam["betas"], adam["eps"], st["step"]
+        stream = c.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        self._lib.check(L.lp_exchange_step(c.byref(a), stream))
+
     def all_reduce(self):
         """Sum over the ranks, in place, on torch's current stream."""
         L, c = self._lib.lib(), self._ctypes
         stream = c.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        if self.fused and self.use_fused and self.one_launch:
+            return self.exchange_step()
         self.handle.barrier(channel=0)                       # every rank's backward has finished
         if self.fused and self.use_fused:
             mc = c.c_void_p(self.multicast_ptr) if self.mode == "multimem" else None
