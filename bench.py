@@ -480,7 +480,9 @@ def measure(args, env, w, full):
     set_bytes = sum(t.numel() * t.element_size() for t in (sets[0].tex, sets[0].grad_image, sets[0].image, sets[0].mask,
                                                            sets[0].uv, sets[0].grad_tex))
 
-    stream = torch.cuda.Stream(device)
+    # the main stream carries the step's dependent chain (texture fetch -> backward -> exchange): its kernels go first
+    # whenever an SM has room (LP_MAIN_PRIORITY=0: default priority)
+    stream = torch.cuda.Stream(device, priority=-1 if os.environ.get("LP_MAIN_PRIORITY", "1") == "1" else 0)
     graphs = None
     with torch.cuda.stream(stream):
         for s in sets:                                   # first touch + correctness of the call chain
@@ -512,7 +514,14 @@ def measure(args, env, w, full):
     geom_done = [torch.cuda.Event() for _ in sets]
     prep_done = [torch.cuda.Event() for _ in sets]
     set_free = [torch.cuda.Event() for _ in sets]
-    pipe_state = {"primed": [False] * len(sets)}
+    bwd_done = [torch.cuda.Event() for _ in sets]
+    pipe_state = {"primed": [False] * len(sets), "prev": None}
+    # N > 1: the exchange is bound by NVLink, not by the SMs, so the visibility stage of the NEXT step is released when
+    # the backward of this step ends and runs inside the exchange's window — instead of next to the texture fetch and
+    # the backward, which are on the step's critical chain (fetch -> backward -> exchange) and slow down when they share
+    # the SMs with it (LP_GATE_RASTER=0: free-running)
+    gate_raster = world > 1 and os.environ.get("LP_GATE_RASTER", "1") == "1"
+    gate_prep = world > 1 and os.environ.get("LP_GATE_PREP", "0") == "1"       # the same for geometry + bins of step k + 2 (measured worse: 134 vs 109 us at 4 GPUs)
     h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if pipeline else None
     h_rast = ctypes.c_void_p(rast_stream.cuda_stream) if pipe_deep else None
     h_main = ctypes.c_void_p(stream.cuda_stream)
@@ -529,10 +538,14 @@ def measure(args, env, w, full):
         k = i % len(sets)
         if pipe_state["primed"][k]:
             prep_stream.wait_event(set_free[k])          # the workspace of set k is free again
+        if gate_prep and pipe_state["prev"] is not None:
+            prep_stream.wait_event(bwd_done[pipe_state["prev"]])
         if pipe_deep:
             sets[k].prepare(h_prep, False)
             geom_done[k].record(prep_stream)
             rast_stream.wait_event(geom_done[k])
+            if gate_raster and pipe_state["prev"] is not None:
+                rast_stream.wait_event(bwd_done[pipe_state["prev"]])
             sets[k].raster(h_rast)
             prep_done[k].record(rast_stream)
         else:
@@ -540,6 +553,8 @@ def measure(args, env, w, full):
             prep_done[k].record(prep_stream)
         stream.wait_event(prep_done[k])
         sets[k].shade_backward(h_main, stream, pipe_raster)
+        bwd_done[k].record(stream)
+        pipe_state["prev"] = k
         if with_exchange:
             exchange(k)
         set_free[k].record(stream)
@@ -560,6 +575,7 @@ def measure(args, env, w, full):
                 stream.wait_stream(prep_stream)
                 torch.cuda.synchronize(device)
                 pipe_state["primed"] = [False] * len(sets)
+                pipe_state["prev"] = None
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
                     prep_stream.wait_stream(stream)
@@ -572,10 +588,12 @@ def measure(args, env, w, full):
                         stream.wait_stream(rast_stream)
                 pipe_graph = g
                 pipe_state["primed"] = [False] * len(sets)
+                pipe_state["prev"] = None
         except Exception as exc:
             print(f"bench.py: pipelined graph capture failed ({exc}); running the pipeline eagerly", file=sys.stderr)
             pipe_graph = None
             pipe_state["primed"] = [False] * len(sets)
+            pipe_state["prev"] = None
 
     def local_step(i):
         """One step without the exchange (rank-local keep-busy loop)."""
