@@ -58,6 +58,8 @@ WORKLOADS = {
                label="configs[3]: sphere.obj subdivided 5x F=1310720, 3ch 1024^2 texture, 1024x1024, 16 views/GPU, "
                      "latent_paint flavour, bilinear"),
 }
+# configs[4] (the end-to-end SDS step) is driven by tools/train_step.py; ``--workload c5`` runs it and prints its line
+C5_LABEL = "configs[4]: end-to-end train_latent_paint_mesh SDS step, renderer in the loop, random-init UNet in PyTorch"
 FOV = np.pi / 3                       # latent_paint flavour (render.py:11)
 FOV_BODY, LOOK_AT_BODY = np.pi / 4, -0.3   # latent_paint_mesh flavour, body camera (render.py:18-19, 33)
 
@@ -755,13 +757,39 @@ def measure(args, env, w, full):
     return res
 
 
+def run_train_step(args):
+    """BASELINE.json configs[4]: the slimmed reference training loop of tools/train_step.py (renderer -> guidance UNet ->
+    backward -> exchange -> fused Adam), 8 views per GPU."""
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "configs[4] times the SD UNet on a GPU; the CPU arm covers the render path (configs[1-3])"}), flush=True)
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import train_step
+    out = train_step.run(views=8, steps=args.steps, warmup=args.warmup, quiet=True)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is None:
+        return None
+    line = {"metric": "views/sec (end-to-end SDS step)", "value": out["views_per_s"], "unit": "views/s", "n_gpus": out["n_gpus"],
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": out["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 renderer / bf16 guidance network", "data": "synthetic",
+            "config": {"workload": out["workload"], "views_per_gpu_per_step": 8, "exchange": out["exchange"]},
+            "stage_ms": out["ms"], "renderer_ms": out["renderer_ms"], "renderer_share_of_step": out["renderer_share_of_step"],
+            "note": out["note"]}
+    print(json.dumps(line), flush=True)
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--sets", type=int, default=4, help="rotating buffer sets (working set > L2)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "off", "geometry", "raster", "deep"],
@@ -779,9 +807,11 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[2] strong-scaling measurement of the default run")
     ap.add_argument("--cpu-views", type=int, default=160, help="views timed for cpu_baseline, about 10-30 s of CPU work (0 = skip)")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload == "c5":
+        return run_train_step(args)
+    w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
 
