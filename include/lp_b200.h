@@ -49,12 +49,12 @@ extern "C" {
 enum {
     LP_OK = 0,
     LP_ERR_BAD_ARG = 1,      /* null pointer, non-positive size, inconsistent shapes */
-    LP_ERR_UNSUPPORTED = 2,  /* e.g. bicubic interpolation, too many channels */
+    LP_ERR_UNSUPPORTED = 2,  /* e.g. too many channels, sizes beyond the index range */
     LP_ERR_WORKSPACE = 3,    /* workspace missing or smaller than lp_workspace_bytes() */
     LP_ERR_CUDA = 4          /* a CUDA runtime call failed; see lp_last_error() */
 };
 
-enum { LP_INTERP_NEAREST = 0, LP_INTERP_BILINEAR = 1 };
+enum { LP_INTERP_NEAREST = 0, LP_INTERP_BILINEAR = 1, LP_INTERP_BICUBIC = 2 };   /* F.grid_sample modes the reference accepts (render.py:9) */
 
 /* LpForwardArgs.flags / LpBackwardArgs.flags */
 enum {
@@ -73,6 +73,12 @@ enum {
     LP_FLAG_GRAD_INTERLEAVED = 1u << 6, /* lp_render_backward with a workspace: leave the gradient in the workspace as
                                            (Th,Tw,4) texel-interleaved float4 and do not touch grad_texture —
                                            lp_allreduce_unpack sums it over the ranks and writes the planar gradient */
+    /* The open points of the kaolin restatement as switches; 0 = the decree.  The same
+       switches exist in oracle/raster_ref.c and oracle/kaolin_shim.py, so a diff against real kaolin is a flag flip */
+    LP_FLAG_BBOX_HALF_OPEN   = 1u << 7,  /* bounding-box test xmin <= x0 < xmax, ymin <= y0 < ymax instead of the closed box */
+    LP_FLAG_PLAIN_EPS        = 1u << 8,  /* s += eps instead of s += copysign(eps, s) */
+    LP_FLAG_AFFINE_INTERP    = 1u << 9,  /* screen-space interpolation: z0 = sum w_k z_k, w'_k = w_k, instead of perspective-correct */
+    LP_FLAG_SH_BAND1_XZY     = 1u << 10, /* SH band-1 axis order (x, z, y) instead of (y, z, x) */
     LP_FLAG_MICRO_OFF        = 1u << 22, /* never / always rasterize small faces face-parallel in the setup kernel */
     LP_FLAG_MICRO_ON         = 1u << 23  /* (default: on when the mesh has at least one face per 16 pixels) */
     /* bits 24-30: stop-after-stage ablation switches, compiled in only with -DLP_PROFILE (tools/), ignored otherwise */
@@ -208,6 +214,19 @@ int lp_render_shade(const LpForwardArgs *args, void *stream);
 int lp_render_raster_shade(const LpForwardArgs *args, void *stream);   /* raster + shade in the one fused tile kernel */
 int lp_render_backward(const LpBackwardArgs *args, void *stream);
 int lp_texture_map_forward(const LpTextureMapArgs *args, void *stream);
+/* The resize to the latent grid that follows the render in TexturedMeshModel.render_train (src/latent_paint/models/
+ * textured_mesh.py:214-218: F.interpolate(x, (64, 64), mode='bicubic') on mask, background, foreground and image) as one
+ * launch over up to eight (planes, H, W) -> (planes, OH, OW) tensors, with ATen's upsample_bicubic2d arithmetic
+ * (align_corners=False).  backward != 0: `in` holds the upstream gradients (planes, OH, OW), `out` the gradients at
+ * (planes, H, W), ACCUMULATED into (the caller zeroes them). */
+typedef struct LpResizeArgs {
+    const float *in[8];
+    float       *out[8];
+    int32_t      planes[8];        /* B * C of each tensor */
+    int32_t      n, H, W, OH, OW, backward;
+} LpResizeArgs;
+int lp_resize_bicubic(const LpResizeArgs *args, void *stream);
+
 /* planar (C,Th,Tw) texture -> (Th,Tw,4) texel-interleaved float4 for LpForwardArgs.texture_rgba (16 * Th * Tw bytes);
  * repack whenever the texture changes (after the optimiser step) */
 int lp_pack_texture(const float *texture, int32_t C, int32_t Th, int32_t Tw, void *texture_rgba, void *stream);

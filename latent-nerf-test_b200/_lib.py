@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 LP_OK, LP_ERR_BAD_ARG, LP_ERR_UNSUPPORTED, LP_ERR_WORKSPACE, LP_ERR_CUDA = 0, 1, 2, 3, 4
-LP_INTERP_NEAREST, LP_INTERP_BILINEAR = 0, 1
+LP_INTERP_NEAREST, LP_INTERP_BILINEAR, LP_INTERP_BICUBIC = 0, 1, 2
 LP_FLAG_MASK_IMAGE = 1 << 0
 LP_FLAG_WHITE_BACKGROUND = 1 << 1
 LP_FLAG_REJECT_BEHIND = 1 << 2
@@ -30,6 +30,10 @@ LP_FLAG_CULL_NZ_ZERO = 1 << 3
 LP_FLAG_SHADE_FEATURES = 1 << 4
 LP_FLAG_GRAD_OVERWRITE = 1 << 5
 LP_FLAG_GRAD_INTERLEAVED = 1 << 6
+LP_FLAG_BBOX_HALF_OPEN = 1 << 7
+LP_FLAG_PLAIN_EPS = 1 << 8
+LP_FLAG_AFFINE_INTERP = 1 << 9
+LP_FLAG_SH_BAND1_XZY = 1 << 10
 LP_FLAG_MICRO_OFF = 1 << 22
 LP_FLAG_MICRO_ON = 1 << 23
 LP_OPT_PDL = 1
@@ -38,7 +42,7 @@ LP_OPT_EXCHANGE_CTAS = 3
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step", "lp_resize_bicubic"]
 
 
 class LpForwardArgs(Structure):
@@ -93,6 +97,11 @@ class LpExchangeArgs(Structure):
 
 
 LP_EXCHANGE_FLAG_BYTES = 8192
+
+
+class LpResizeArgs(Structure):
+    _fields_ = [("inp", c_void_p * 8), ("out", c_void_p * 8), ("planes", c_int32 * 8),
+                ("n", c_int32), ("H", c_int32), ("W", c_int32), ("OH", c_int32), ("OW", c_int32), ("backward", c_int32)]
 
 
 class LpTextureMapArgs(Structure):
@@ -175,6 +184,8 @@ def lib() -> ctypes.CDLL:
     L.lp_pack_texture.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     L.lp_exchange_step.restype = c_int32
     L.lp_exchange_step.argtypes = [POINTER(LpExchangeArgs), c_void_p]
+    L.lp_resize_bicubic.restype = c_int32
+    L.lp_resize_bicubic.argtypes = [POINTER(LpResizeArgs), c_void_p]
     L.lp_set_option.restype = c_int32
     L.lp_set_option.argtypes = [c_int32, c_int32]
     L.lp_timing_collect.restype = c_int32

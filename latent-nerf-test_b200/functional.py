@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._lib import LpBackwardArgs, LpForwardArgs
 
-_INTERP = {"nearest": _lib.LP_INTERP_NEAREST, "bilinear": _lib.LP_INTERP_BILINEAR}
+_INTERP = {"nearest": _lib.LP_INTERP_NEAREST, "bilinear": _lib.LP_INTERP_BILINEAR, "bicubic": _lib.LP_INTERP_BICUBIC}
 
 #: kernel launches enqueued by this process through the wrappers below (bench.py reads it)
 launch_counter = {"kernels": 0}
@@ -164,7 +164,7 @@ class _RenderTexture(torch.autograd.Function):
         if texture.dim() != 4 or texture.shape[0] != 1:
             raise ValueError(f"texture_map must have shape (1,C,T,T), got {tuple(texture.shape)}")
         if cfg.interp not in _INTERP:
-            raise ValueError(f"lp_b200: interpolation mode '{cfg.interp}' is not implemented (nearest, bilinear)")
+            raise ValueError(f"lp_b200: interpolation mode '{cfg.interp}' is not implemented (nearest, bilinear, bicubic)")
         tex = texture.detach().to(torch.float32).contiguous()
         _, C, Th, Tw = tex.shape
         B, H, W = cfg.B, cfg.H, cfg.W
@@ -417,7 +417,7 @@ class _TextureMap(torch.autograd.Function):
     def forward(ctx, texture_maps, uv, mode):
         _require_cuda(texture_maps, "texture_maps")
         if mode not in _INTERP:
-            raise ValueError(f"lp_b200: interpolation mode '{mode}' is not implemented (nearest, bilinear)")
+            raise ValueError(f"lp_b200: interpolation mode '{mode}' is not implemented (nearest, bilinear, bicubic)")
         device = texture_maps.device
         tex = texture_maps.detach().to(torch.float32).contiguous()
         uvc = uv.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -458,3 +458,68 @@ class _TextureMap(torch.autograd.Function):
 
 def texture_map(uv, texture_maps, mode="nearest"):
     return _TextureMap.apply(texture_maps, uv, mode)
+
+
+class _ResizeBicubic(torch.autograd.Function):
+    """``F.interpolate(x, size, mode='bicubic')`` (align_corners=False) of several equally sized (B,C_i,H,W) tensors in
+    one launch, forward and backward (``lp_resize_bicubic``)."""
+
+    @staticmethod
+    def _launch(ins, outs, H, W, OH, OW, backward, device):
+        a = _lib.LpResizeArgs()
+        a.n, a.H, a.W, a.OH, a.OW, a.backward = len(ins), H, W, OH, OW, int(backward)
+        for i, (x, y) in enumerate(zip(ins, outs)):
+            a.inp[i], a.out[i], a.planes[i] = x.data_ptr(), y.data_ptr(), x.shape[0] * x.shape[1]
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().lp_resize_bicubic(ctypes.byref(a), _stream(device)))
+            launch_counter["kernels"] += 1
+
+    @staticmethod
+    def forward(ctx, size, *tensors):
+        device = tensors[0].device
+        _require_cuda(tensors[0], "resize input")
+        xs = [t.detach().to(torch.float32).contiguous() for t in tensors]
+        H, W = xs[0].shape[-2:]
+        if any(x.dim() != 4 or tuple(x.shape[-2:]) != (H, W) for x in xs) or len(xs) > 8:
+            raise ValueError("resize_bicubic: up to eight (B,C,H,W) tensors of one spatial size")
+        OH, OW = size
+        outs = [torch.empty(x.shape[0], x.shape[1], OH, OW, dtype=torch.float32, device=device) for x in xs]
+        _ResizeBicubic._launch(xs, outs, H, W, OH, OW, False, device)
+        ctx.shape = (H, W, OH, OW)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        H, W, OH, OW = ctx.shape
+        idx = [i for i, g in enumerate(grads) if g is not None and ctx.needs_input_grad[i + 1]]
+        res = [None] * len(grads)
+        if idx:
+            device = grads[idx[0]].device
+            gs = [grads[i].to(torch.float32).contiguous() for i in idx]
+            outs = [torch.zeros(g.shape[0], g.shape[1], H, W, dtype=torch.float32, device=device) for g in gs]
+            _ResizeBicubic._launch(gs, outs, H, W, OH, OW, True, device)
+            for i, o in zip(idx, outs):
+                res[i] = o
+        return (None, *res)
+
+
+def resize_bicubic(tensors, size):
+    """[(B,C_i,H,W), ...] -> [(B,C_i,size[0],size[1]), ...]: torch's bicubic ``F.interpolate`` for all of them in one launch."""
+    return list(_ResizeBicubic.apply(tuple(int(s) for s in size), *tensors))
+
+
+def depth_for_guidance(depth, size=64, normalised=True):
+    """The depth input of depth-conditioned guidance (reference ``src/stable_diffusion_depth.py:302-319``:
+    ``train_step(text, inputs, depth_mask)`` resizes ``depth_mask`` to 64 x 64 with bicubic ``F.interpolate`` and min-max
+    normalises the whole tensor to [-1, 1]) from the rasterizer's depth buffer.  ``depth`` (B,H,W): camera-space z of
+    the visible surface (< 0), 0 where nothing is covered.  The map is MiDaS-like inverse distance, ``1 / -z`` on the
+    surface and 0 on the background (nearer = larger), resized by ``lp_resize_bicubic`` and normalised.
+    -> (B,1,size,size)."""
+    d = depth.to(torch.float32)
+    inv = torch.where(d < 0, -1.0 / d.clamp(max=-1e-12), torch.zeros_like(d))[:, None].contiguous()
+    if inv.shape[-1] != size or inv.shape[-2] != size:
+        inv = resize_bicubic([inv], (size, size))[0]
+    if normalised:
+        lo, hi = inv.min(), inv.max()
+        inv = 2.0 * (inv - lo) / (hi - lo) - 1.0
+    return inv

@@ -19,6 +19,10 @@ import torch
 from . import _lib, camera, functional, meshio
 
 REJECT_BEHIND_CAMERA = True      # BASELINE.md decree 3
+# the other open points of the restatement as switches, mirrored in oracle/kaolin_shim.py (False = the decree)
+BBOX_HALF_OPEN = False
+PLAIN_EPS = False
+AFFINE_INTERP = False
 
 
 # ---------------------------------------------------------------- render.camera
@@ -35,12 +39,41 @@ def index_vertices_by_faces(vertices_features, faces):
 
 
 def uniform_laplacian(num_vertices, faces):
+    """``kal.ops.mesh.uniform_laplacian``: dense (V,V), as the reference calls it (textured_mesh.py:62).  Use
+    :func:`uniform_laplacian_sparse` for anything beyond a few thousand vertices."""
     adj = torch.zeros((num_vertices, num_vertices), dtype=torch.float32, device=faces.device)
     for a, b in ((0, 1), (1, 2), (2, 0)):
         adj[faces[:, a], faces[:, b]] = 1
         adj[faces[:, b], faces[:, a]] = 1
     deg = adj.sum(dim=1, keepdim=True).clamp(min=1)
     return adj / deg - torch.eye(num_vertices, device=faces.device)
+
+
+def uniform_laplacian_sparse(num_vertices, faces):
+    """The same operator as a sparse CSR tensor: 1/deg(i) on the neighbours of vertex i, -1 on the diagonal — 7 entries
+    per vertex on a closed triangle mesh instead of V (the dense form of the reference, latent_paint_mesh
+    textured_mesh.py:60-71, is 1.7 TB at config 4's 655 362 vertices).  ``laplacian_coordinates`` / ``lap_loss`` below are
+    the two places the reference uses it (``L.mm(vertices)``, :65 and :314-317)."""
+    f = faces.long()
+    src = torch.cat([f[:, 0], f[:, 1], f[:, 1], f[:, 2], f[:, 2], f[:, 0]])
+    dst = torch.cat([f[:, 1], f[:, 0], f[:, 2], f[:, 1], f[:, 0], f[:, 2]])
+    key = torch.unique(src * num_vertices + dst)                       # each undirected edge once per direction
+    row, col = key // num_vertices, key % num_vertices
+    deg = torch.bincount(row, minlength=num_vertices).clamp(min=1).to(torch.float32)
+    diag = torch.arange(num_vertices, device=faces.device)
+    rows = torch.cat([row, diag]); cols = torch.cat([col, diag])
+    vals = torch.cat([1.0 / deg[row], -torch.ones(num_vertices, device=faces.device)])
+    return torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (num_vertices, num_vertices)).coalesce().to_sparse_csr()
+
+
+def laplacian_coordinates(L, vertices):
+    """``L.mm(vertices)`` for the dense or the sparse operator."""
+    return torch.sparse.mm(L, vertices) if L.layout != torch.strided else L.mm(vertices)
+
+
+def lap_loss(L, vertices, init_lap):
+    """``torch.mean(torch.sum((L.mm(v) - init_lap) ** 2))`` (reference latent_paint_mesh textured_mesh.py:314-317)."""
+    return torch.mean(torch.sum((laplacian_coordinates(L, vertices) - init_lap) ** 2))
 
 
 # ---------------------------------------------------------------- render.mesh
@@ -78,7 +111,9 @@ def rasterize(height, width, face_vertices_z, face_vertices_image, face_features
     feats = [f.to(device).float().expand(B, -1, -1, -1) if f.shape[0] == 1 and B > 1 else f.to(device).float() for f in feats]
     dims = [f.shape[-1] for f in feats]
     ff = torch.cat(feats, dim=-1) if len(feats) > 1 else feats[0]
-    flags = _lib.LP_FLAG_MASK_IMAGE | (_lib.LP_FLAG_REJECT_BEHIND if REJECT_BEHIND_CAMERA else 0)
+    flags = _lib.LP_FLAG_MASK_IMAGE | (_lib.LP_FLAG_REJECT_BEHIND if REJECT_BEHIND_CAMERA else 0) | \
+        (_lib.LP_FLAG_BBOX_HALF_OPEN if BBOX_HALF_OPEN else 0) | (_lib.LP_FLAG_PLAIN_EPS if PLAIN_EPS else 0) | \
+        (_lib.LP_FLAG_AFFINE_INTERP if AFFINE_INTERP else 0)
     cfg = functional.RenderConfig(
         verts=None, faces=None, cameras=None, proj=(1.0, 1.0, -1.0), H=int(height), W=int(width), flags=flags,
         multiplier=1000.0 if multiplier is None else float(multiplier), eps=1e-8 if eps is None else float(eps),
@@ -157,6 +192,7 @@ def make_module() -> types.ModuleType:
     mesh.prepare_vertices, mesh.rasterize, mesh.dibr_rasterization = prepare_vertices, rasterize, dibr_rasterization
     mesh.texture_mapping, mesh.spherical_harmonic_lighting = texture_mapping, spherical_harmonic_lighting
     ops_mesh.index_vertices_by_faces, ops_mesh.uniform_laplacian = index_vertices_by_faces, uniform_laplacian
+    ops_mesh.uniform_laplacian_sparse = uniform_laplacian_sparse        # (extension: not a kaolin name)
     io_obj.import_mesh = import_mesh
     io_off.import_mesh = import_off_mesh
     render.camera, render.mesh, ops.mesh, io.obj, io.off = cam, mesh, ops_mesh, io_obj, io_off

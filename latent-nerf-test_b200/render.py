@@ -7,8 +7,8 @@ kaolin + ATen.  Differences, all additive:
   * ``renderer.last_buffers`` holds the visibility buffers of the last call when
     ``renderer.keep_buffers`` is set (face_idx int32, bary, depth, uv) — the reference
     returns no depth / face index, the tuple arity is unchanged;
-  * ``interpolation_mode='bicubic'`` passes the constructor assert like in the reference but
-    raises ``ValueError`` at render time (not implemented).
+  * all three interpolation modes of the reference's assert (nearest / bilinear / bicubic) are implemented; bicubic
+    takes the split forward (footprint kernel + ``k_shade``), the other two the fused one.
 """
 from __future__ import annotations
 
@@ -16,6 +16,14 @@ import numpy as np
 import torch
 
 from . import _lib, camera, functional
+
+
+def decree_flags(r) -> int:
+    """LP_FLAG_* bits of the decree switches set on a renderer object."""
+    return (_lib.LP_FLAG_BBOX_HALF_OPEN if getattr(r, "bbox_half_open", False) else 0) | \
+        (_lib.LP_FLAG_PLAIN_EPS if getattr(r, "plain_eps", False) else 0) | \
+        (_lib.LP_FLAG_AFFINE_INTERP if getattr(r, "affine_interpolation", False) else 0) | \
+        (_lib.LP_FLAG_SH_BAND1_XZY if getattr(r, "sh_band1_xzy", False) else 0)
 
 
 class Renderer:
@@ -31,6 +39,11 @@ class Renderer:
         self.dim = dim
         self.background = torch.ones(dim).to(self.device).float()
         self.reject_behind_camera = True   # BASELINE.md decree 3
+        # the other open points of the kaolin restatement, False = the decree; the oracle has
+        # the same switches (oracle/kaolin_shim.py), so a diff against real kaolin is a flag flip
+        self.bbox_half_open = False        # bounding-box test x0 < xmax, y0 < ymax instead of <=
+        self.plain_eps = False             # s + eps instead of s + copysign(eps, s)
+        self.affine_interpolation = False  # screen-space instead of perspective-correct interpolation
         self.keep_buffers = False
         self.last_buffers = {}
 
@@ -45,7 +58,7 @@ class Renderer:
             flags |= _lib.LP_FLAG_WHITE_BACKGROUND
         if self.reject_behind_camera:
             flags |= _lib.LP_FLAG_REJECT_BEHIND
-        return flags
+        return flags | decree_flags(self)
 
     def _config(self, verts, faces, elev, azim, radius, look_at_height, dims, white_background):
         cam = self.get_camera_from_view(torch.tensor(elev), torch.tensor(azim), r=radius,
@@ -54,6 +67,14 @@ class Renderer:
             verts=functional._f32(verts, self.device), faces=functional._faces_i32(faces, self.device, verts.shape[0]),
             cameras=cam.contiguous(), proj=self._proj, H=int(dims[1]), W=int(dims[0]),
             flags=self._flags(white_background), interp=self.interpolation_mode, want_buffers=self.keep_buffers)
+
+    def depth_map(self, size=64, normalised=True):
+        """``(B,1,size,size)`` depth input for depth-conditioned guidance (reference ``src/stable_diffusion_depth.py:302-319``)
+        of the last render: inverse distance on the surface, 0 on the background, bicubic resize to ``size``, min-max
+        normalised to [-1, 1] over the batch as ``train_step`` does.  Needs ``keep_buffers = True`` during the render."""
+        if "depth" not in self.last_buffers or self.last_buffers["depth"] is None:
+            raise RuntimeError("depth_map() needs renderer.keep_buffers = True before the render call")
+        return functional.depth_for_guidance(self.last_buffers["depth"], size, normalised)
 
     def render_single_view(self, mesh, face_attributes, elev=0, azim=0, radius=2, look_at_height=0.0):
         """Per-face-vertex colours ``(1,F,3,Cf)`` → ``(image (1,Cf,H,W), mask (1,1,H,W))``

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, camera, functional
+from .render import decree_flags
 
 
 class Renderer:
@@ -39,6 +40,9 @@ class Renderer:
         self.lights = lights.unsqueeze(0).to(self.device)
         self._lights_flat = self.lights.reshape(-1).to(torch.float32).contiguous()
         self.reject_behind_camera = True
+        # decree switches (see latent-nerf-test_b200/render.py): False = BASELINE.md's decree
+        self.bbox_half_open = self.plain_eps = self.affine_interpolation = False
+        self.sh_band1_xzy = False          # SH band-1 axis order (x, z, y) instead of the decreed (y, z, x)
         self.keep_buffers = False
         self.last_buffers = {}
 
@@ -71,6 +75,14 @@ class Renderer:
                                                     B, V, F, functional._ptr(out), functional._stream(self.device)))
         return out
 
+    def depth_map(self, size=64, normalised=True):
+        """``(B,1,size,size)`` depth input for depth-conditioned guidance (reference ``src/stable_diffusion_depth.py:302-319``)
+        of the last render: inverse distance on the surface, 0 on the background, bicubic resize to ``size``, min-max
+        normalised to [-1, 1] over the batch as ``train_step`` does.  Needs ``keep_buffers = True`` during the render."""
+        if "depth" not in self.last_buffers or self.last_buffers["depth"] is None:
+            raise RuntimeError("depth_map() needs renderer.keep_buffers = True before the render call")
+        return functional.depth_for_guidance(self.last_buffers["depth"], size, normalised)
+
     def render_single_view(self, *args, **kwargs):
         raise NotImplementedError("dead code in the reference (latent_paint_mesh/models/render.py:107-157 unpacks "
                                   "three tensors from kaolin's two-tuple rasterize and has no caller)")
@@ -93,6 +105,7 @@ class Renderer:
             flags |= _lib.LP_FLAG_WHITE_BACKGROUND
         if self.reject_behind_camera:
             flags |= _lib.LP_FLAG_REJECT_BEHIND
+        flags |= decree_flags(self)
         cfg = functional.RenderConfig(
             verts=functional._f32(verts, self.device), faces=functional._faces_i32(faces, self.device, verts.shape[0]),
             cameras=cam.contiguous(), proj=self._proj[P], H=int(dims[1]), W=int(dims[0]), flags=flags,

@@ -6,7 +6,8 @@ Only the render call chain is mirrored; the model class itself (parameters, chec
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
+
+from . import functional
 
 
 def render_train(renderer, mesh, face_attributes, texture_img, env_sphere, background_sphere_colors, theta, phi, radius,
@@ -26,9 +27,7 @@ def render_train(renderer, mesh, face_attributes, texture_img, env_sphere, backg
         elev=theta, azim=phi, radius=radius, look_at_height=dy)
     mask = mask.detach()
     if latent_mode and mask.shape[-1] != 64:
-        # the reference resizes to the 64 x 64 latent grid with torch's bicubic filter (:214-218); same call here
-        mask = F.interpolate(mask, (64, 64), mode='bicubic')
-        pred_back = F.interpolate(pred_back, (64, 64), mode='bicubic')
-        pred_features = F.interpolate(pred_features, (64, 64), mode='bicubic')
-        pred_map = F.interpolate(pred_map, (64, 64), mode='bicubic')
+        # the reference resizes to the 64 x 64 latent grid with four bicubic F.interpolate calls (:214-218); here one
+        # launch (lp_resize_bicubic: ATen's upsample_bicubic2d arithmetic) over all four tensors, forward and backward
+        mask, pred_back, pred_features, pred_map = functional.resize_bicubic([mask, pred_back, pred_features, pred_map], (64, 64))
     return {'image': pred_map, 'mask': mask, 'background': pred_back, 'foreground': pred_features}

@@ -43,6 +43,16 @@ import torch
 RASTER_IMPL = os.environ.get("LP_ORACLE_RASTER", "bbox")
 #: decree 3 of BASELINE.md §4: faces whose interpolated depth is not < 0 never win a pixel
 REJECT_BEHIND_CAMERA = True
+#: the other open points of the decree as switches (defaults = the decree; a diff against real kaolin is a flag flip):
+#: half-open bounding box (x0 < xmax, y0 < ymax), plain ``s + eps`` instead of ``s + copysign(eps, s)``, screen-space
+#: (affine) instead of perspective-correct interpolation.  ``SH_BAND1_AXES`` below is the fourth.
+BBOX_HALF_OPEN = False
+PLAIN_EPS = False
+AFFINE_INTERP = False
+
+
+def decree_flags():
+    return int(REJECT_BEHIND_CAMERA) | (2 if BBOX_HALF_OPEN else 0) | (4 if PLAIN_EPS else 0) | (8 if AFFINE_INTERP else 0)
 DEFAULT_MULTIPLIER = 1000.0
 DEFAULT_EPS = 1e-8
 
@@ -164,7 +174,7 @@ def _rasterize_c(H, W, fvz, fvi, valid, mult, eps, impl):
     fn = _lib().lp_ref_rasterize_brute if impl == "brute" else _lib().lp_ref_rasterize_bbox
     fn(B, F, H, W, 0, fvz_c.data_ptr(), fvi_c.data_ptr(), None,
        valid_c.data_ptr() if valid_c is not None else None,
-       ctypes.c_float(mult), ctypes.c_float(eps), int(REJECT_BEHIND_CAMERA),
+       ctypes.c_float(mult), ctypes.c_float(eps), decree_flags(),
        None, face_idx.data_ptr(), w.data_ptr(), depth.data_ptr())
     return face_idx, w, depth
 
@@ -202,24 +212,34 @@ def _rasterize_torch(H, W, fvz, fvi, valid, mult, eps, block=32):
                 y0 = rows[j0:j1][:, None, None]
                 g = lambda t: t[b, idx][None, None, :]
                 Xa, Ya, Xb, Yb, Xc, Yc = g(xa), g(ya), g(xb), g(yb), g(xc), g(yc)
-                inbox = (g(xmin) <= x0) & (x0 <= g(xmax)) & (g(ymin) <= y0) & (y0 <= g(ymax))
+                if BBOX_HALF_OPEN:
+                    inbox = (g(xmin) <= x0) & (x0 < g(xmax)) & (g(ymin) <= y0) & (y0 < g(ymax))
+                else:
+                    inbox = (g(xmin) <= x0) & (x0 <= g(xmax)) & (g(ymin) <= y0) & (y0 <= g(ymax))
                 w0 = (Xb - x0) * (Yc - y0) - (Yb - y0) * (Xc - x0)
                 w1 = (Xc - x0) * (Ya - y0) - (Yc - y0) * (Xa - x0)
                 w2 = (Xa - x0) * (Yb - y0) - (Ya - y0) * (Xb - x0)
                 s = (w0 + w1) + w2
-                s = s + torch.copysign(epsv, s)
+                s = s + (epsv if PLAIN_EPS else torch.copysign(epsv, s))
                 w0, w1, w2 = w0 / s, w1 / s, w2 / s
-                q = (w0 / g(za) + w1 / g(zb)) + w2 / g(zc)
-                z0 = 1.0 / q
+                if AFFINE_INTERP:
+                    z0 = (w0 * g(za) + w1 * g(zb)) + w2 * g(zc)
+                else:
+                    q = (w0 / g(za) + w1 / g(zb)) + w2 / g(zc)
+                    z0 = 1.0 / q
                 hit = inbox & (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
                 hit = hit & ((z0 < 0) if REJECT_BEHIND_CAMERA else (z0 == z0))
                 key = torch.where(hit, z0, torch.full_like(z0, float("-inf")))
                 best, arg = torch.max(key, dim=2)            # first maximal value = lowest face index
                 anyhit = hit.any(dim=2)
                 sel = arg[..., None]
-                pw = torch.stack([(torch.gather(w0, 2, sel)[..., 0] / za[b, idx][arg]) * best,
-                                  (torch.gather(w1, 2, sel)[..., 0] / zb[b, idx][arg]) * best,
-                                  (torch.gather(w2, 2, sel)[..., 0] / zc[b, idx][arg]) * best], dim=-1)
+                if AFFINE_INTERP:
+                    pw = torch.stack([torch.gather(w0, 2, sel)[..., 0], torch.gather(w1, 2, sel)[..., 0],
+                                      torch.gather(w2, 2, sel)[..., 0]], dim=-1)
+                else:
+                    pw = torch.stack([(torch.gather(w0, 2, sel)[..., 0] / za[b, idx][arg]) * best,
+                                      (torch.gather(w1, 2, sel)[..., 0] / zb[b, idx][arg]) * best,
+                                      (torch.gather(w2, 2, sel)[..., 0] / zc[b, idx][arg]) * best], dim=-1)
                 face_idx[b, j0:j1, i0:i1] = torch.where(anyhit, idx[arg], torch.full_like(arg, -1))
                 wout[b, j0:j1, i0:i1] = torch.where(anyhit[..., None], pw, torch.zeros_like(pw))
                 depth[b, j0:j1, i0:i1] = torch.where(anyhit, best, torch.zeros_like(best))

@@ -25,6 +25,14 @@
  *   w'_k  = (w_k / z_k) * z0
  *   feat_d= (w'_0 f_a,d + w'_1 f_b,d) + w'_2 f_c,d
  *
+ * The open points of the decree are switches (bits of the `reject_behind` argument, which is a flag word):
+ *   1  reject_behind   a face whose interpolated depth is not < 0 never wins (decree 3)
+ *   2  half-open bbox  xmin <= x0 < xmax, ymin <= y0 < ymax instead of the closed box
+ *   4  plain eps       s += eps instead of s += copysign(eps, s)
+ *   8  affine          screen-space interpolation: z0 = (w0 za + w1 zb) + w2 zc and w'_k = w_k, instead of the
+ *                      perspective-correct 1 / sum(w_k / z_k)
+ * Default (1) is the decree of BASELINE.md; the others exist so that a diff against real kaolin is a flag flip.
+ *
  * Two traversals that must give identical results (tests check it):
  *   lp_ref_rasterize_brute : per pixel, every face in index order (normative)
  *   lp_ref_rasterize_bbox  : per face, the pixels of its bounding box, z-buffer with the tie rule
@@ -54,17 +62,27 @@ static void load_face(const float *fvz, const float *fvi, float mult, face_rec *
 
 /* One (pixel, face) evaluation.  Returns 1 when the face covers the pixel and passes the
  * behind-camera rule; then *z0 and w[3] (the perspective-correct weights w') are set. */
-static inline int eval_face(const face_rec *r, float x0, float y0, float eps, int reject_behind,
+static inline int eval_face(const face_rec *r, float x0, float y0, float eps, int flags,
                             float *z0_out, float w_out[3])
 {
-    if (!(r->xmin <= x0 && x0 <= r->xmax && r->ymin <= y0 && y0 <= r->ymax)) return 0;
+    const int reject_behind = flags & 1, half_open = flags & 2, plain_eps = flags & 4, affine = flags & 8;
+    if (half_open) { if (!(r->xmin <= x0 && x0 < r->xmax && r->ymin <= y0 && y0 < r->ymax)) return 0; }
+    else if (!(r->xmin <= x0 && x0 <= r->xmax && r->ymin <= y0 && y0 <= r->ymax)) return 0;
     float w0 = (r->xb - x0) * (r->yc - y0) - (r->yb - y0) * (r->xc - x0);
     float w1 = (r->xc - x0) * (r->ya - y0) - (r->yc - y0) * (r->xa - x0);
     float w2 = (r->xa - x0) * (r->yb - y0) - (r->ya - y0) * (r->xb - x0);
     float s = (w0 + w1) + w2;
-    s = s + copysignf(eps, s);
+    s = s + (plain_eps ? eps : copysignf(eps, s));
     w0 = w0 / s; w1 = w1 / s; w2 = w2 / s;
     if (!(w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f)) return 0;
+    if (affine) {
+        float za0 = (w0 * r->za + w1 * r->zb) + w2 * r->zc;
+        if (reject_behind) { if (!(za0 < 0.0f)) return 0; }
+        else if (za0 != za0) return 0;
+        *z0_out = za0;
+        w_out[0] = w0; w_out[1] = w1; w_out[2] = w2;
+        return 1;
+    }
     float q = (w0 / r->za + w1 / r->zb) + w2 / r->zc;
     float z0 = 1.0f / q;
     if (reject_behind) { if (!(z0 < 0.0f)) return 0; }

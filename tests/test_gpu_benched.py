@@ -258,3 +258,151 @@ def test_bin_overflow_cascade_and_rerun(pdl):
             assert torch.equal(face_idx, first)
     finally:
         _lib.check(L.lp_set_option(_lib.LP_OPT_PDL, 1))
+
+
+def test_decree_switches_flip_kernel_and_oracle_together():
+    """The open points of the kaolin restatement are runtime switches in the kernels, in oracle/raster_ref.c and in
+    oracle/kaolin_shim.py.  Each one, flipped in both places, must keep face_idx / depth / barycentrics bit-identical
+    and the pixels within tolerance — and must actually change something."""
+    verts, faces, uv = scene("blub", 0.6, 0.25)
+    tex = rnd((1, 4, 64, 64), 1, 0.4).to(DEV)
+    view = dict(elev=1.0, azim=0.7, radius=1.25, look_at_height=0.25)
+    base = {}
+    try:
+        for name, attr in (("decree", None), ("half_open", "BBOX_HALF_OPEN"), ("plain_eps", "PLAIN_EPS"), ("affine", "AFFINE_INTERP")):
+            r = lp.LatentPaintRenderer(DEV, dim=(160, 128), interpolation_mode="bilinear")
+            r.keep_buffers = True
+            r.bbox_half_open, r.plain_eps, r.affine_interpolation = name == "half_open", name == "plain_eps", name == "affine"
+            kal.BBOX_HALF_OPEN, kal.PLAIN_EPS, kal.AFFINE_INTERP = r.bbox_half_open, r.plain_eps, r.affine_interpolation
+            image, mask = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, **view)
+            ref = renderer_ref.LatentPaintRendererRef(dim=(160, 128), interpolation_mode="bilinear")
+            oi, om = ref.render_single_view_texture(verts, faces, uv, tex.cpu(), **view)
+            assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ref.last["face_idx"]), name
+            assert torch.equal(r.last_buffers["depth"].cpu(), kal.LAST["depth"]), name
+            assert torch.equal(r.last_buffers["bary"].cpu(), kal.LAST["bary"]), name
+            assert_close(image, oi, f"image ({name})")
+            base[name] = (r.last_buffers["depth"].clone(), r.last_buffers["bary"].clone())
+        assert not torch.equal(base["affine"][0], base["decree"][0]) and not torch.equal(base["affine"][1], base["decree"][1])
+        # screen-space barycentrics sum to one up to rounding, like the perspective-correct ones
+        cov = r.last_buffers["face_idx"] >= 0
+        assert_close(base["affine"][1].sum(-1)[cov], torch.ones(int(cov.sum())), "affine barycentrics sum to one", atol=1e-5)
+
+        kal.BBOX_HALF_OPEN = kal.PLAIN_EPS = kal.AFFINE_INTERP = False
+        # half-open box: a triangle whose right-most / lowest vertices sit exactly on pixel centres (kaolin-level entry,
+        # already projected vertices: W = H = 8 puts pixel centres at multiples of 0.125 + 0.0625... in NDC * 1000 = exact)
+        kc = lp.kaolin_compat.make_module()
+        fvi = torch.tensor([[[[-0.375, 0.375], [0.375, 0.375], [0.375, -0.375]]]])      # pixel centres (col 2, row 2), (5, 2), (5, 5)
+        fvz = torch.full((1, 1, 3), -1.0)
+        feat = torch.ones(1, 1, 3, 1)
+        got = {}
+        for ho in (False, True):
+            lp.kaolin_compat.BBOX_HALF_OPEN = kal.BBOX_HALF_OPEN = ho
+            _, idx = kc.render.mesh.rasterize(8, 8, fvz.to(DEV), fvi.to(DEV), feat.to(DEV))
+            _, oidx = kal.rasterize(8, 8, fvz, fvi, feat)
+            assert torch.equal(idx.cpu(), oidx), f"half_open={ho}"
+            got[ho] = int((idx >= 0).sum())
+        assert got[True] < got[False], "the half-open box must drop the pixels on the box's far edges"
+        lp.kaolin_compat.BBOX_HALF_OPEN = kal.BBOX_HALF_OPEN = False
+
+        # SH band-1 order: mesh flavour lighting with a light that tells x from y
+        vm, fm, um = scene("sphere", 1.0, 0.0)
+        lights = torch.tensor([0.5, 0.9, 0.0, 0.1, 0.0, 0.0, 0.0, 0.0, 0.0])
+        th, ph, ra = torch.tensor([1.2, 1.6]), torch.tensor([0.3, 2.0]), torch.tensor([1.8, 2.0])
+        out = {}
+        for xzy in (False, True):
+            rm = lp.LatentPaintMeshRenderer(DEV, dim=(64, 64), lights=lights)
+            rm.sh_band1_xzy = xzy
+            kal.SH_BAND1_AXES = (0, 2, 1) if xzy else (1, 2, 0)
+            o = rm.render_single_view_texture(vm.to(DEV), fm.to(DEV), um.to(DEV), tex, th, ph, ra, dims=(64, 64))
+            ro = renderer_ref.LatentPaintMeshRendererRef(dim=(64, 64), lights=lights).render_single_view_texture(
+                vm, fm, um, tex.cpu(), th, ph, ra, dims=(64, 64))
+            assert_close(o[3], ro[3], f"lighting (band-1 xzy={xzy})")
+            out[xzy] = o[3].clone()
+        assert float((out[True] - out[False]).abs().max()) > 1e-2
+    finally:
+        kal.BBOX_HALF_OPEN = kal.PLAIN_EPS = kal.AFFINE_INTERP = False
+        kal.SH_BAND1_AXES = (1, 2, 0)
+        lp.kaolin_compat.BBOX_HALF_OPEN = False
+
+
+def test_bicubic_texture_fetch_vs_oracle():
+    """The third interpolation mode the reference's Renderer accepts (render.py:9, used at :64): ATen's bicubic
+    grid_sample (A = -0.75, unclipped coordinate, per-tap border clamp), forward and backward, through the Renderer
+    (blub: UVs inside the unit square; and UVs pushed outside it so taps clamp at the border) and through the operator API."""
+    verts, faces, uv = scene("blub", 0.6, 0.25)
+    view = dict(elev=1.0, azim=0.7, radius=1.25, look_at_height=0.25)
+    for uvs, C, T, dims, white in ((uv, 4, 128, (64, 64), False), (uv * 1.6 - 0.3, 3, 37, (120, 88), True)):
+        tex = rnd((1, C, T, T), 1, 0.4)
+        g = rnd((1, C, dims[1], dims[0]), 2)
+        tg = tex.to(DEV).requires_grad_(True)
+        r = lp.LatentPaintRenderer(DEV, dim=dims, interpolation_mode="bicubic")
+        r.keep_buffers = True
+        ig, mg = r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uvs.to(DEV), tg, white_background=white, **view)
+        ig.backward(g.to(DEV))
+        tc = tex.clone().requires_grad_(True)
+        ref = renderer_ref.LatentPaintRendererRef(dim=dims, interpolation_mode="bicubic")
+        oi, om = ref.render_single_view_texture(verts, faces, uvs, tc, white_background=white, **view)
+        oi.backward(g)
+        assert torch.equal(r.last_buffers["face_idx"].cpu().long(), ref.last["face_idx"]) and torch.equal(mg.cpu(), om)
+        # sixteen taps with weights in [-0.07, 0.6] whose magnitudes sum to at most 1.5625^2 (see the resize test)
+        assert_close(ig, oi, "bicubic image", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
+        assert_close(tg.grad, tc.grad, "bicubic texture gradient", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
+    kc = lp.kaolin_compat.make_module()
+    coords = torch.rand(2, 40, 24, 2, generator=torch.Generator().manual_seed(3)) * 1.2 - 0.1
+    maps = rnd((2, 3, 21, 17), 4)
+    mg = maps.to(DEV).requires_grad_(True)
+    out = kc.render.mesh.texture_mapping(coords.to(DEV), mg, mode="bicubic")
+    go = rnd(tuple(out.shape), 5)
+    out.backward(go.to(DEV))
+    mc = maps.clone().requires_grad_(True)
+    oo = kal.texture_mapping(coords, mc, mode="bicubic")
+    oo.backward(go)
+    assert_close(out, oo, "texture_mapping bicubic", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
+    assert_close(mg.grad, mc.grad, "texture_mapping bicubic gradient", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
+
+
+def test_fused_bicubic_resize_and_depth_map():
+    """SURVEY.md 8 f ranks 1 and 3.  (1) ``lp_resize_bicubic``: the four bicubic ``F.interpolate(x, (64, 64))`` calls of
+    ``TexturedMeshModel.render_train`` (reference src/latent_paint/models/textured_mesh.py:214-218) as one launch, forward
+    and backward, against torch on the CPU.  (2) ``renderer.depth_map()``: the (B,1,64,64) min-max normalised depth input
+    of depth-conditioned guidance (src/stable_diffusion_depth.py:302-319) against the same steps on the oracle's depth."""
+    import torch.nn.functional as F
+    xs = [rnd((2, c, 96, 80), 10 + c) for c in (1, 4, 4, 3)]
+    gs = [rnd((2, c, 64, 64), 20 + c) for c in (1, 4, 4, 3)]
+    xg = [x.to(DEV).requires_grad_(i != 0) for i, x in enumerate(xs)]                  # the mask carries no gradient
+    ys = lp.functional.resize_bicubic(xg, (64, 64))
+    sum((y * g.to(DEV)).sum() for y, g in zip(ys, gs)).backward()
+    xc = [x.clone().requires_grad_(i != 0) for i, x in enumerate(xs)]
+    yc = [F.interpolate(x, (64, 64), mode="bicubic") for x in xc]
+    sum((y * g).sum() for y, g in zip(yc, gs)).backward()
+    for i in range(4):
+        assert_close(ys[i], yc[i], f"resized tensor {i}", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
+        if i:
+            assert_close(xg[i].grad, xc[i].grad, f"gradient through the resize {i}", rtol=1e-4, atol=1e-5 * 4)
+    assert xg[0].grad is None
+    up = lp.functional.resize_bicubic([xs[1].to(DEV)], (200, 100))[0]                # enlarging works the same way
+    assert_close(up, F.interpolate(xs[1], (200, 100), mode="bicubic"), "upsampled", rtol=1e-4, atol=1e-5 * 1.5625 ** 2)
+
+    verts, faces, uv = scene("teddy", 1.0, 0.0)
+    radius, theta, phi = mesh_views_local(3)
+    tex = rnd((1, 4, 64, 64), 1).to(DEV)
+    for dims in ((64, 64), (128, 96)):
+        r = lp.LatentPaintMeshRenderer(DEV, dim=dims)
+        r.keep_buffers = True
+        r.render_single_view_texture(verts.to(DEV), faces.to(DEV), uv.to(DEV), tex, theta, phi, radius, dims=dims)
+        dm = r.depth_map(size=64)
+        assert dm.shape == (3, 1, 64, 64) and abs(float(dm.min()) + 1) < 1e-6 and abs(float(dm.max()) - 1) < 1e-6
+        ref = renderer_ref.LatentPaintMeshRendererRef(dim=dims)
+        ref.render_single_view_texture(verts, faces, uv, tex.cpu(), theta, phi, radius, dims=dims)
+        z = kal.LAST["depth"]
+        assert torch.equal(r.last_buffers["depth"].cpu(), z)
+        inv = torch.where(z < 0, -1.0 / z.clamp(max=-1e-12), torch.zeros_like(z))[:, None]
+        if dims != (64, 64):
+            inv = F.interpolate(inv, size=(64, 64), mode="bicubic", align_corners=False)   # stable_diffusion_depth.py:310
+        want = 2.0 * (inv - inv.min()) / (inv.max() - inv.min()) - 1.0                      # :313
+        assert_close(dm, want, f"depth map {dims}", rtol=1e-4, atol=2e-5)
+
+
+def mesh_views_local(B):
+    from tests.common import mesh_views
+    return mesh_views(B, seed=11)

@@ -308,16 +308,15 @@ def test_c_abi_error_codes_on_device():
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_WORKSPACE
     ws = torch.empty(need, dtype=torch.uint8, device=DEV)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-    a.interp = 2
+    a.interp = 3                                # 0 / 1 / 2 = nearest / bilinear / bicubic
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_ERR_UNSUPPORTED
     a.interp = 0
     assert L.lp_render_forward(ctypes.byref(a), stream) == _lib.LP_OK
     assert L.lp_last_launch_count() == 4        # setup + binning, large-face binning, footprint classification, footprint kernel
     torch.cuda.synchronize()
     assert float(mask.sum()) > 0
-    r = lp.LatentPaintRenderer(DEV, dim=(32, 32), interpolation_mode="bicubic")
-    with pytest.raises(ValueError, match="not implemented"):
-        r.render_single_view_texture(v, faces.to(DEV), uv.to(DEV), tex, elev=1.0, azim=0.5, radius=1.3)
+    with pytest.raises(AssertionError):
+        lp.LatentPaintRenderer(DEV, dim=(32, 32), interpolation_mode="lanczos")
     with pytest.raises(RuntimeError, match="no CPU path"):
         lp.LatentPaintRenderer(DEV, dim=(32, 32)).render_single_view_texture(v, faces.to(DEV), uv.to(DEV), tex.cpu())
 
