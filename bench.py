@@ -166,6 +166,11 @@ class DeviceStep:
         b.C, b.Th, b.Tw, b.interp = C, T, T, a.interp
         b.grad_texture = self.grad_tex.data_ptr()
         b.footprint_any = self.footprint_any.data_ptr()
+        if not mesh_flavour and os.environ.get("LP_BWD_WORKLIST", "1") == "1":
+            # this set's forward workspace is its own: the backward may walk the forward's list of live footprints
+            wl, wc = ctypes.c_void_p(), ctypes.c_void_p()
+            _lib.check(L.lp_forward_worklist(ctypes.byref(a), ctypes.byref(wl), ctypes.byref(wc)))
+            b.worklist, b.worklist_ctrl = wl, wc
         if accum is not None:
             # N > 1, fused exchange: the accumulation buffer lives in symmetric memory next to the planar gradient;
             # the backward leaves the gradient interleaved and lp_allreduce_unpack reduces + unpacks + broadcasts it

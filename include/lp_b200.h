@@ -168,6 +168,11 @@ typedef struct LpBackwardArgs {
     uint64_t       workspace_bytes;
     const float   *under_mask;     /* optional (B,1,H,W), face-feature path: grad_image is dL/d composed and is scaled
                                       by (1 - under_mask) per pixel (the backward of the fused composition) */
+    /* optional (both or none; LP_FLAG_MASK_IMAGE): the forward call's list of live footprints, from
+       lp_forward_worklist(), valid while that call's workspace has not been reused.  The backward then visits the
+       listed footprints directly instead of scanning the coverage flags of all of them */
+    const void    *worklist;
+    const void    *worklist_ctrl;
 } LpBackwardArgs;
 
 /* kal.render.mesh.texture_mapping forward (latent_paint render.py:64, latent_paint_mesh render.py:243):
@@ -182,6 +187,9 @@ typedef struct LpTextureMapArgs {
 } LpTextureMapArgs;
 
 int         lp_version(void);
+/* builds with -DLP_CHECKED test the kernels' index and capacity invariants on the device: number of violations since the
+ * library was loaded (0 in ordinary builds), *first_line = source line of the first; synchronises the device */
+int         lp_check_failures(int *first_line);
 /* process-wide switches.  LP_OPT_PDL (default 1): chain the kernels of a call with programmatic dependent launch
  * (each kernel's prologue overlaps its predecessor's tail); 0 = plain stream-ordered launches.
  * LP_OPT_RASTER_CTAS_PER_SM (default 0 = all the tile kernel's launch bounds allow): resident CTAs per SM of the
@@ -199,6 +207,8 @@ int lp_cameras_from_views(const float *elev, const float *azim, const float *rad
                           float look_at_height, int32_t B, float *cameras, void *stream);
 
 uint64_t    lp_backward_workspace_bytes(int32_t C, int32_t Th, int32_t Tw);
+/* where in `args->workspace` the forward leaves its live-footprint list (for LpBackwardArgs.worklist / worklist_ctrl) */
+int lp_forward_worklist(const LpForwardArgs *args, const void **worklist, const void **worklist_ctrl);
 
 int lp_render_forward(const LpForwardArgs *args, void *stream);
 /* lp_render_forward split in three, so a caller can overlap everything that does not read the texture

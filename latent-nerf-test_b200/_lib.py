@@ -42,7 +42,7 @@ LP_OPT_EXCHANGE_CTAS = 3
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step", "lp_resize_bicubic"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step", "lp_resize_bicubic", "lp_check_failures", "lp_forward_worklist"]
 
 
 class LpForwardArgs(Structure):
@@ -75,6 +75,7 @@ class LpBackwardArgs(Structure):
         ("grad_face_features", c_void_p), ("footprint_any", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_uint64),
         ("under_mask", c_void_p),
+        ("worklist", c_void_p), ("worklist_ctrl", c_void_p),
     ]
 
 
@@ -186,6 +187,10 @@ def lib() -> ctypes.CDLL:
     L.lp_exchange_step.argtypes = [POINTER(LpExchangeArgs), c_void_p]
     L.lp_resize_bicubic.restype = c_int32
     L.lp_resize_bicubic.argtypes = [POINTER(LpResizeArgs), c_void_p]
+    L.lp_check_failures.restype = c_int32
+    L.lp_check_failures.argtypes = [POINTER(c_int32)]
+    L.lp_forward_worklist.restype = c_int32
+    L.lp_forward_worklist.argtypes = [POINTER(LpForwardArgs), POINTER(c_void_p), POINTER(c_void_p)]
     L.lp_set_option.restype = c_int32
     L.lp_set_option.argtypes = [c_int32, c_int32]
     L.lp_timing_collect.restype = c_int32

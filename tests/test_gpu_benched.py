@@ -17,7 +17,7 @@ import latent_nerf_test_b200 as lp
 from latent_nerf_test_b200 import _lib
 from oracle import kaolin_shim as kal
 from oracle import renderer_ref
-from tests.common import assert_close, assert_texture_grad_close, fp64_corner_texel, rnd, scene
+from tests.common import accumulation_terms, assert_close, assert_texture_grad_close, fp64_corner_texel, rnd, scene
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -152,7 +152,8 @@ def test_config3_mesh_flavour_B64_vs_oracle():
         assert_close(got, want, name)
     n, rms, ref64 = fp64_corner_texel(ref.last["uv"], t, g, ofi)
     assert n > 10000, "the background texel must be a real accumulation in this test"
-    assert_texture_grad_close(st.grad_tex, t.grad[0], "texture gradient (64 views)", background=(n, rms, ref64))
+    assert_texture_grad_close(st.grad_tex, t.grad[0], "texture gradient (64 views)", background=(n, rms, ref64),
+                              terms=accumulation_terms(ref.last["uv"], g, t.shape))
 
 
 def test_config4_full_size_one_view_vs_oracle():
