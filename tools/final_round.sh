@@ -2,12 +2,14 @@
 # End-of-round evidence on one GPU: parity tests, the default bench line, the ncu launch list of the same command
 # (eager launches) and one --set full capture of every kernel of the step.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2 | tee gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/smoke.log
-python bench.py > gpurun_out/bench_final.log 2> gpurun_out/bench_final.err; tail -c 600 gpurun_out/bench_final.log
-python bench.py --pipeline off --no-e2e --cpu-views 0 > gpurun_out/bench_serial.log 2>/dev/null
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_20.log 2> gpurun_out/bench_20.err; tail -c 300 gpurun_out/bench_20.err
+python bench.py > gpurun_out/bench_final.log 2> gpurun_out/bench_final.err; tail -c 3000 gpurun_out/bench_final.log
+python bench.py --pipeline off --no-e2e --no-strong --cpu-views 0 > gpurun_out/bench_serial.log 2>/dev/null
+for w in c3 c4; do python bench.py --workload $w --no-e2e --no-strong --cpu-views 0 --steps 50 > gpurun_out/bench_$w.log 2>gpurun_out/bench_$w.err; done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv \
-    python bench.py --steps 4 --warmup 3 --no-graph --no-e2e --cpu-views 0 > gpurun_out/ncu1.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"k_" --launch-skip 42 -c 14 -f -o gpurun_out/prof_final \
-    python bench.py --steps 4 --warmup 3 --no-graph --no-e2e --cpu-views 0 > gpurun_out/ncu2.log 2>&1
+    python bench.py --steps 4 --warmup 3 --no-graph --no-e2e --no-strong --cpu-views 0 > gpurun_out/ncu1.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"k_" --launch-skip ${NCU_SKIP:-30} -c ${NCU_COUNT:-12} -f -o gpurun_out/prof_final \
+    python bench.py --steps 4 --warmup 3 --no-graph --no-e2e --no-strong --cpu-views 0 > gpurun_out/ncu2.log 2>&1
 tail -2 gpurun_out/ncu2.log
