@@ -829,7 +829,7 @@ def main():
     if args.pipeline != "off":
         _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_RASTER_CTAS_PER_SM, 2))
     for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM),
-                      ("LP_EXCHANGE_CTAS", _lib.LP_OPT_EXCHANGE_CTAS)):
+                      ("LP_EXCHANGE_CTAS", _lib.LP_OPT_EXCHANGE_CTAS), ("LP_WALK_CTAS", _lib.LP_OPT_WALK_CTAS_PER_SM)):
         if os.environ.get(name):
             _lib.check(_lib.lib().lp_set_option(opt, int(os.environ[name])))
     res = measure(args, env, w, full=True)

@@ -190,11 +190,16 @@ int         lp_version(void);
 /* builds with -DLP_CHECKED test the kernels' index and capacity invariants on the device: number of violations since the
  * library was loaded (0 in ordinary builds), *first_line = source line of the first; synchronises the device */
 int         lp_check_failures(int *first_line);
+/* -DLP_PROFILE builds: per-warp trace of the footprint kernel's last launch, 16 words per warp (entry, after the
+ * dependency wait, exit in ns of %globaltimer; footprints, candidates, longest footprint in clocks and its candidates,
+ * sum of footprint clocks, clocks in staging / exact evaluation / shading, evaluation rounds); returns the number of words copied, 0 in production builds */
+int         lp_debug_trace(unsigned long long *out, int words);
 /* process-wide switches.  LP_OPT_PDL (default 1): chain the kernels of a call with programmatic dependent launch
  * (each kernel's prologue overlaps its predecessor's tail); 0 = plain stream-ordered launches.
  * LP_OPT_RASTER_CTAS_PER_SM (default 0 = all the tile kernel's launch bounds allow): resident CTAs per SM of the
  * persistent tile kernel; fewer leave room for kernels of other streams to run beside it */
-enum { LP_OPT_PDL = 1, LP_OPT_RASTER_CTAS_PER_SM = 2, LP_OPT_EXCHANGE_CTAS = 3 /* CTAs of lp_exchange_step, 0 = one per SM */ };
+enum { LP_OPT_PDL = 1, LP_OPT_RASTER_CTAS_PER_SM = 2, LP_OPT_EXCHANGE_CTAS = 3 /* CTAs of lp_exchange_step, 0 = one per SM */,
+       LP_OPT_WALK_CTAS_PER_SM = 4 /* CTAs per SM of lp_render_shade / lp_render_backward, 0 = eight */ };
 int         lp_set_option(int option, int value);
 const char *lp_last_error(void);
 const char *lp_error_string(int code);

@@ -39,10 +39,11 @@ LP_FLAG_MICRO_ON = 1 << 23
 LP_OPT_PDL = 1
 LP_OPT_RASTER_CTAS_PER_SM = 2
 LP_OPT_EXCHANGE_CTAS = 3
+LP_OPT_WALK_CTAS_PER_SM = 4
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",
-           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step", "lp_resize_bicubic", "lp_check_failures", "lp_forward_worklist"]
+           "lp_last_launch_count", "lp_timing_enable", "lp_timing_collect", "lp_backward_workspace_bytes", "lp_texture_map_forward", "lp_render_prepare", "lp_render_raster", "lp_render_shade", "lp_render_raster_shade", "lp_allreduce_multimem", "lp_allreduce_p2p", "lp_allreduce_unpack", "lp_adam_step", "lp_render_step_host_async", "lp_set_option", "lp_pack_texture", "lp_exchange_step", "lp_resize_bicubic", "lp_check_failures", "lp_forward_worklist", "lp_debug_trace"]
 
 
 class LpForwardArgs(Structure):

@@ -6,6 +6,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3 * 1024 * 1024
+from latent_nerf_test_b200 import _lib
+if os.environ.get("LP_EXCHANGE_CTAS"):         # CTAs of the one-launch exchange (default: one per SM)
+    _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_EXCHANGE_CTAS, int(os.environ["LP_EXCHANGE_CTAS"])))
 sb = SymmetricGradientBuffer(n, dev)
 plain = torch.zeros(n, device=dev)
 def timed(fn, iters=200):
