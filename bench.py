@@ -158,6 +158,8 @@ class DeviceStep:
             a.face_normals, a.vertex_normals = self.fn.data_ptr(), self.vn.data_ptr()
             a.lights, a.normals, a.lighting = self.lights.data_ptr(), self.normals.data_ptr(), self.lighting.data_ptr()
             self.keep += [off, vf]
+        if os.environ.get("LP_MICRO") in ("0", "1"):     # experiments: force the micro-face path off / on (default: the density rule)
+            a.flags |= _lib.LP_FLAG_MICRO_ON if os.environ["LP_MICRO"] == "1" else _lib.LP_FLAG_MICRO_OFF
         if os.environ.get("LP_DEBUG_FWD_STOP"):      # only honoured by -DLP_PROFILE builds (tools/)
             a.flags |= 1 << int(os.environ["LP_DEBUG_FWD_STOP"])
         b = _lib.LpBackwardArgs()
@@ -829,7 +831,8 @@ def main():
     if args.pipeline != "off":
         _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_RASTER_CTAS_PER_SM, 2))
     for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM),
-                      ("LP_EXCHANGE_CTAS", _lib.LP_OPT_EXCHANGE_CTAS), ("LP_WALK_CTAS", _lib.LP_OPT_WALK_CTAS_PER_SM)):
+                      ("LP_EXCHANGE_CTAS", _lib.LP_OPT_EXCHANGE_CTAS), ("LP_WALK_CTAS", _lib.LP_OPT_WALK_CTAS_PER_SM),
+                      ("LP_EXCHANGE_BULK", _lib.LP_OPT_EXCHANGE_BULK)):
         if os.environ.get(name):
             _lib.check(_lib.lib().lp_set_option(opt, int(os.environ[name])))
     res = measure(args, env, w, full=True)

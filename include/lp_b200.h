@@ -199,7 +199,8 @@ int         lp_debug_trace(unsigned long long *out, int words);
  * LP_OPT_RASTER_CTAS_PER_SM (default 0 = all the tile kernel's launch bounds allow): resident CTAs per SM of the
  * persistent tile kernel; fewer leave room for kernels of other streams to run beside it */
 enum { LP_OPT_PDL = 1, LP_OPT_RASTER_CTAS_PER_SM = 2, LP_OPT_EXCHANGE_CTAS = 3 /* CTAs of lp_exchange_step, 0 = one per SM */,
-       LP_OPT_WALK_CTAS_PER_SM = 4 /* CTAs per SM of lp_render_shade / lp_render_backward, 0 = eight */ };
+       LP_OPT_WALK_CTAS_PER_SM = 4 /* CTAs per SM of lp_render_shade / lp_render_backward, 0 = eight */,
+       LP_OPT_EXCHANGE_BULK = 5 /* peer form of lp_exchange_step reads with bulk asynchronous copies (default 1) */ };
 int         lp_set_option(int option, int value);
 const char *lp_last_error(void);
 const char *lp_error_string(int code);

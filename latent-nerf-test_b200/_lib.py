@@ -40,6 +40,7 @@ LP_OPT_PDL = 1
 LP_OPT_RASTER_CTAS_PER_SM = 2
 LP_OPT_EXCHANGE_CTAS = 3
 LP_OPT_WALK_CTAS_PER_SM = 4
+LP_OPT_EXCHANGE_BULK = 5
 
 EXPORTS = ["lp_version", "lp_last_error", "lp_error_string", "lp_workspace_bytes", "lp_cameras_from_views",
            "lp_render_forward", "lp_render_backward", "lp_vertex_normals", "lp_render_step_host",

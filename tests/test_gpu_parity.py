@@ -502,6 +502,60 @@ def test_allreduce_unpack_single_rank_is_the_unpack():
     assert_close(fused.grad_tex, ref.grad_tex, "gradient through the fused exchange path", rtol=1e-5, atol=1e-6)
 
 
+def test_exchange_step_single_rank_bulk_copies_and_register_loads():
+    """lp_exchange_step with world = 1 over a plain pointer (the in-kernel handshakes have no peer to wait for): the peer
+    form — bulk asynchronous copies (cp.async.bulk + mbarrier) into shared memory — and the register-load form must both
+    leave the planar gradient = the texel-interleaved accumulation buffer transposed, over repeated launches with
+    changing grids (the epoch lives in the flag block, not in per-CTA state), and the optimiser epilogue must equal
+    torch.optim.Adam on that gradient."""
+    L = _lib.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flag_floats = _lib.LP_EXCHANGE_FLAG_BYTES // 4
+    try:
+        for bulk in (1, 0):
+            _lib.check(L.lp_set_option(_lib.LP_OPT_EXCHANGE_BULK, bulk))
+            for C, T in ((3, 256), (4, 100), (1, 32)):
+                ntex = T * T
+                # planar gradient | accumulation buffer | planar parameters | flag block
+                buf = torch.zeros(C * ntex + 4 * ntex + C * ntex + flag_floats, device=DEV)
+                ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=DEV)
+                a = _lib.LpExchangeArgs()
+                a.multicast_base, a.buffer_ptrs_dev = None, ctypes.c_void_p(ptrs.data_ptr())
+                a.accum_offset, a.grad_offset = 4 * C * ntex, 0
+                a.param_offset, a.flags_offset = 4 * (C * ntex + 4 * ntex), 4 * (2 * C * ntex + 4 * ntex)
+                a.ntex, a.C, a.rank, a.world = ntex, C, 0, 1
+                gen = torch.Generator(device=DEV).manual_seed(10 * C + bulk)
+                for it, ctas in enumerate((0, 7, 300, 0)):
+                    _lib.check(L.lp_set_option(_lib.LP_OPT_EXCHANGE_CTAS, ctas))
+                    acc = torch.randn(ntex, 4, device=DEV, generator=gen)
+                    buf[C * ntex:C * ntex + 4 * ntex].copy_(acc.reshape(-1))
+                    _lib.check(L.lp_exchange_step(ctypes.byref(a), stream))
+                    torch.cuda.synchronize()
+                    assert torch.equal(buf[:C * ntex].view(C, ntex), acc[:, :C].t().contiguous()), (bulk, C, T, it)
+                _lib.check(L.lp_set_option(_lib.LP_OPT_EXCHANGE_CTAS, 0))
+                # optimiser epilogue: parameters in the allocation, state local
+                p0 = 0.4 * torch.randn(C, ntex, device=DEV, generator=gen)
+                buf[C * ntex + 4 * ntex:2 * C * ntex + 4 * ntex].copy_(p0.reshape(-1))
+                m, v = torch.zeros(C * ntex, device=DEV), torch.zeros(C * ntex, device=DEV)
+                pref = torch.nn.Parameter(p0.clone())
+                opt = torch.optim.Adam([pref], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+                a.adam, a.exp_avg, a.exp_avg_sq = 1, m.data_ptr(), v.data_ptr()
+                a.lr, a.beta1, a.beta2, a.eps = 0.01, 0.9, 0.99, 1e-15
+                for step in (1, 2, 3):
+                    acc = torch.randn(ntex, 4, device=DEV, generator=gen)
+                    buf[C * ntex:C * ntex + 4 * ntex].copy_(acc.reshape(-1))
+                    a.step = step
+                    _lib.check(L.lp_exchange_step(ctypes.byref(a), stream))
+                    pref.grad = acc[:, :C].t().contiguous()
+                    opt.step()
+                    torch.cuda.synchronize()
+                    assert_close(buf[C * ntex + 4 * ntex:2 * C * ntex + 4 * ntex].view(C, ntex), pref.detach(),
+                                 f"sharded Adam epilogue (bulk={bulk}, C={C})", rtol=1e-5, atol=1e-6)
+    finally:
+        L.lp_set_option(_lib.LP_OPT_EXCHANGE_BULK, 1)
+        L.lp_set_option(_lib.LP_OPT_EXCHANGE_CTAS, 0)
+
+
 def test_fused_render_train_composition():
     """SURVEY.md §8 f rank 1: object render + environment-sphere render + pred_back * (1 - mask) + pred_features * mask
     (reference textured_mesh.py:187-220) through the fused composition, against the vectors frozen from the

@@ -7,6 +7,8 @@ dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3 * 1024 * 1024
 from latent_nerf_test_b200 import _lib
+if os.environ.get("LP_EXCHANGE_BULK"):         # 0: register loads instead of bulk asynchronous copies
+    _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_EXCHANGE_BULK, int(os.environ["LP_EXCHANGE_BULK"])))
 if os.environ.get("LP_EXCHANGE_CTAS"):         # CTAs of the one-launch exchange (default: one per SM)
     _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_EXCHANGE_CTAS, int(os.environ["LP_EXCHANGE_CTAS"])))
 sb = SymmetricGradientBuffer(n, dev)

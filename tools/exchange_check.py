@@ -14,6 +14,8 @@ res = {"world": world}
 for C, T in ((3, 1024), (4, 512)):
     ntex = T * T
     sb = SymmetricGradientBuffer(C * ntex, dev, interleaved_texels=ntex, channels=C, with_params=True)
+    if os.environ.get("LP_CHECK_MODE"):                  # p2p: the peer form (bulk asynchronous copies) where multicast is the default
+        sb.mode = os.environ["LP_CHECK_MODE"]
     res.setdefault("mode", sb.mode)
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     ok = True
