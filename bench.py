@@ -373,6 +373,15 @@ def cpu_reference_views_per_s(w, n_views, seed=0, warmup=0, impl="torch"):
     return n_views / dt, dt
 
 
+def debug_check(tag):
+    """LP_DEBUG_CHECK=1 with a -DLP_CHECKED library: print the device-side violation counter at this point."""
+    if os.environ.get("LP_DEBUG_CHECK") != "1":
+        return
+    torch.cuda.synchronize()
+    line = ctypes.c_int32(0)
+    print(f"[check] {tag}: {_lib.lib().lp_check_failures(ctypes.byref(line))} violations (first at line {line.value})", file=sys.stderr, flush=True)
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -575,32 +584,40 @@ def measure(args, env, w, full):
     PIPE_STEPS = len(sets) * max(2, min(10, args.steps // len(sets)))
     if os.environ.get("LP_PIPE_STEPS"):
         PIPE_STEPS = len(sets) * max(1, int(os.environ["LP_PIPE_STEPS"]) // len(sets))
-    pipe_graph = None
+    pipe_graph, rest_graph = None, None
+    REST_STEPS = args.steps % PIPE_STEPS           # a step count that is not a multiple of the replay length: a second,
+                                                   # shorter graph for the remainder instead of eager launches
     if pipeline and not args.no_graph and (world == 1 or symm_bufs):
+        def capture(n_steps):
+            pipe_state["primed"] = [False] * len(sets)
+            pipe_state["prev"] = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                prep_stream.wait_stream(stream)
+                if pipe_deep:
+                    rast_stream.wait_stream(stream)
+                for i in range(n_steps):
+                    pipelined_step(i)
+                stream.wait_stream(prep_stream)
+                if pipe_deep:
+                    stream.wait_stream(rast_stream)
+            pipe_state["primed"] = [False] * len(sets)
+            pipe_state["prev"] = None
+            return g
         try:
             with torch.cuda.stream(stream):
+                debug_check("before the eager pipelined warm-up")
                 for i in range(PIPE_STEPS):                     # warm both paths before capture
                     pipelined_step(i)
                 stream.wait_stream(prep_stream)
                 torch.cuda.synchronize(device)
-                pipe_state["primed"] = [False] * len(sets)
-                pipe_state["prev"] = None
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream):
-                    prep_stream.wait_stream(stream)
-                    if pipe_deep:
-                        rast_stream.wait_stream(stream)
-                    for i in range(PIPE_STEPS):
-                        pipelined_step(i)
-                    stream.wait_stream(prep_stream)
-                    if pipe_deep:
-                        stream.wait_stream(rast_stream)
-                pipe_graph = g
-                pipe_state["primed"] = [False] * len(sets)
-                pipe_state["prev"] = None
+                debug_check("after the eager pipelined warm-up")
+                pipe_graph = capture(PIPE_STEPS)
+                if REST_STEPS:
+                    rest_graph = capture(REST_STEPS)
         except Exception as exc:
             print(f"bench.py: pipelined graph capture failed ({exc}); running the pipeline eagerly", file=sys.stderr)
-            pipe_graph = None
+            pipe_graph, rest_graph = None, None
             pipe_state["primed"] = [False] * len(sets)
             pipe_state["prev"] = None
 
@@ -621,19 +638,52 @@ def measure(args, env, w, full):
         else:
             exchange(local_step(i))
 
+    def join_side_streams():
+        """Order the side streams behind everything on the main stream and forget the pipeline's event state.  A graph
+        replay lives on the main stream only: eager pipelined steps that follow one must not start their geometry /
+        visibility stages (on the side streams) before the replay's kernels are done with the buffer sets — they did
+        when the step count was not a multiple of the replay length (config 4 with --steps 50: two prepare passes of
+        one set at once, class counters counted twice, work lists overrun)."""
+        if pipeline:
+            prep_stream.wait_stream(stream)
+            if pipe_deep:
+                rast_stream.wait_stream(stream)
+            pipe_state["primed"] = [False] * len(sets)
+            pipe_state["prev"] = None
+
+    def join_main_stream():
+        """The reverse: everything the eager steps left on the side streams precedes what the main stream does next."""
+        if pipeline:
+            stream.wait_stream(prep_stream)
+            if pipe_deep:
+                stream.wait_stream(rast_stream)
+
     def run_steps(n):
         """n steps the way the timed region runs them: whole replays of the pipelined graph, the rest eagerly."""
         if pipe_graph is not None:
+            if n >= PIPE_STEPS:
+                join_main_stream()
             for _ in range(n // PIPE_STEPS):
                 pipe_graph.replay()
             n = n % PIPE_STEPS
+            if n and n == REST_STEPS and rest_graph is not None:
+                join_main_stream()
+                rest_graph.replay()
+                n = 0
+            if n:
+                join_side_streams()
         for i in range(n):
             one_step(i)
 
     with torch.cuda.stream(stream):
         # warm-up: at least `warmup` steps AND at least one replay of every graph the timed region replays, so the
         # first (slow: upload + first-launch initialisation) replay is outside the timed region
+        debug_check("after capture")
         run_steps(max(args.warmup, PIPE_STEPS if pipe_graph is not None else 0))
+        if rest_graph is not None:
+            join_main_stream()
+            rest_graph.replay()
+        debug_check("after the warm-up replays")
         if pipeline:
             stream.wait_stream(prep_stream)
         if pipe_deep:
@@ -659,6 +709,7 @@ def measure(args, env, w, full):
         # keep the GPU busy a little longer if the region was too short for nvidia-smi to sample it
         if sampler and ms < 400:
             t_end = time.time() + 0.5
+            join_side_streams()
             while time.time() < t_end:
                 for i in range(50):
                     local_step(i)              # no collective here: the other ranks are not in this loop
@@ -836,6 +887,11 @@ def main():
         if os.environ.get(name):
             _lib.check(_lib.lib().lp_set_option(opt, int(os.environ[name])))
     res = measure(args, env, w, full=True)
+    if os.environ.get("LP_B200_LIB"):                    # a -DLP_CHECKED library counts violated kernel invariants on the device
+        line = ctypes.c_int32(0)
+        n_bad = _lib.lib().lp_check_failures(ctypes.byref(line))
+        if n_bad:
+            print(f"bench.py: {n_bad} violated kernel invariants, first at lp_b200.cu:{line.value}", file=sys.stderr)
     strong = None
     if args.workload == "c2" and not args.no_strong and WORKLOADS["c3"]["B"] % env.world == 0:
         # BASELINE.json configs[2] beside the weak-scaling line: 64 teddy views in total, sharded over the ranks
