@@ -552,10 +552,20 @@ def measure(args, env, w, full):
             else:
                 dist.all_reduce(sets[k].grad_tex)
 
-    def pipelined_step(i, with_exchange=True):
-        k = i % len(sets)
+    # N > 1, deep pipeline: the visibility stage of step i + 1 is issued during step i and released by the backward of
+    # step i - 1, so it runs in the window of exchange i - 1 (NVLink-bound, SMs idle) and is complete before the texture
+    # fetch of step i + 1 asks for it — instead of being released by backward i, which put it in front of that fetch
+    # (LP_RASTER_LOOKAHEAD=0: the former schedule; measured at 2 GPUs: 110 us per step, free-running 99 us)
+    lookahead_on = gate_raster and pipe_deep and os.environ.get("LP_RASTER_LOOKAHEAD", "1") == "1"
+    prep_after_bwd = world > 1 and os.environ.get("LP_PREP_AFTER_BWD", "0") == "1"      # measured worse at 2 GPUs: 94.7 vs 90.5 us per step
+    pipe_state["front"] = [False] * len(sets)
+
+    def issue_front(k):
+        """Geometry + bins (and visibility / uv) of buffer set k on the side streams."""
         if pipe_state["primed"][k]:
-            prep_stream.wait_event(set_free[k])          # the workspace of set k is free again
+            # the workspace of set k is free again: after its exchange — or, N > 1, already after its backward (the
+            # exchange touches the gradient buffers only), which lets this pass start inside the exchange's window
+            prep_stream.wait_event(bwd_done[k] if prep_after_bwd else set_free[k])
         if gate_prep and pipe_state["prev"] is not None:
             prep_stream.wait_event(bwd_done[pipe_state["prev"]])
         if pipe_deep:
@@ -569,6 +579,16 @@ def measure(args, env, w, full):
         else:
             sets[k].prepare(h_prep, pipe_raster)
             prep_done[k].record(prep_stream)
+        pipe_state["front"][k] = True
+
+    def pipelined_step(i, with_exchange=True, more=False):
+        """Step i.  ``more``: step i + 1 follows in the same batch (graph or loop), its front may be issued now."""
+        k = i % len(sets)
+        if not pipe_state["front"][k]:
+            issue_front(k)
+        if more and lookahead_on:
+            issue_front((i + 1) % len(sets))             # gated on the backward of step i - 1 (pipe_state["prev"])
+        pipe_state["front"][k] = False
         stream.wait_event(prep_done[k])
         sets[k].shade_backward(h_main, stream, pipe_raster)
         bwd_done[k].record(stream)
@@ -590,6 +610,7 @@ def measure(args, env, w, full):
     if pipeline and not args.no_graph and (world == 1 or symm_bufs):
         def capture(n_steps):
             pipe_state["primed"] = [False] * len(sets)
+            pipe_state["front"] = [False] * len(sets)
             pipe_state["prev"] = None
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
@@ -597,11 +618,12 @@ def measure(args, env, w, full):
                 if pipe_deep:
                     rast_stream.wait_stream(stream)
                 for i in range(n_steps):
-                    pipelined_step(i)
+                    pipelined_step(i, more=i + 1 < n_steps)
                 stream.wait_stream(prep_stream)
                 if pipe_deep:
                     stream.wait_stream(rast_stream)
             pipe_state["primed"] = [False] * len(sets)
+            pipe_state["front"] = [False] * len(sets)
             pipe_state["prev"] = None
             return g
         try:
@@ -619,6 +641,7 @@ def measure(args, env, w, full):
             print(f"bench.py: pipelined graph capture failed ({exc}); running the pipeline eagerly", file=sys.stderr)
             pipe_graph, rest_graph = None, None
             pipe_state["primed"] = [False] * len(sets)
+            pipe_state["front"] = [False] * len(sets)
             pipe_state["prev"] = None
 
     def local_step(i):
@@ -649,6 +672,7 @@ def measure(args, env, w, full):
             if pipe_deep:
                 rast_stream.wait_stream(stream)
             pipe_state["primed"] = [False] * len(sets)
+            pipe_state["front"] = [False] * len(sets)
             pipe_state["prev"] = None
 
     def join_main_stream():
