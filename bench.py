@@ -313,6 +313,11 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
 
     def run(self):
+        # The first query waits 5 ms: spawning nvidia-smi stalls this process (fork of a process with a CUDA context) and
+        # the query itself disturbs the GPU for a few hundred microseconds — measured on the 20-step run (1.3 ms timed
+        # region): 66 us per step without a query inside it, 81 us with one.  Regions shorter than that are followed by the
+        # same steps repeated for half a second (measure()), which is where their clock samples come from.
+        self.stop_flag.wait(0.005)
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
