@@ -561,7 +561,10 @@ def measure(args, env, w, full):
     # step i - 1, so it runs in the window of exchange i - 1 (NVLink-bound, SMs idle) and is complete before the texture
     # fetch of step i + 1 asks for it — instead of being released by backward i, which put it in front of that fetch
     # (LP_RASTER_LOOKAHEAD=0: the former schedule; measured at 2 GPUs: 110 us per step, free-running 99 us)
-    lookahead_on = gate_raster and pipe_deep and os.environ.get("LP_RASTER_LOOKAHEAD", "1") == "1"
+    # (only where the exchange's window is long enough to hold a visibility pass: with the 4 MiB payload of configs[2]
+    # the early release only adds contention to the fetch -> backward chain: 57.9 vs 48.5 us per step at 2 GPUs)
+    lookahead_default = "1" if 16 * T * T >= (8 << 20) else "0"
+    lookahead_on = gate_raster and pipe_deep and os.environ.get("LP_RASTER_LOOKAHEAD", lookahead_default) == "1"
     prep_after_bwd = world > 1 and os.environ.get("LP_PREP_AFTER_BWD", "0") == "1"      # measured worse at 2 GPUs: 94.7 vs 90.5 us per step
     pipe_state["front"] = [False] * len(sets)
 
