@@ -14,7 +14,11 @@ the default run also appends the configs[2] strong-scaling measurement as ``stro
   value      device-timed views/s, inputs resident in HBM, steps replayed from CUDA graphs (the graph is
              uploaded and replayed once during warm-up); by default a three-stream pipeline (geometry |
              visibility | texture fetch + backward + exchange) overlaps the texture-independent stages
-             of later steps (--pipeline off: serial)
+             of later steps (--pipeline off: serial).  A step count that is not a multiple of the replay
+             length (up to 40 steps) replays a second, shorter graph for the remainder.  At N > 1 the exchange
+             is one kernel launch on the main stream (handshakes inside); with an exchange window long enough
+             to hold it, the visibility stage of step i + 1 is issued one step ahead and released by the
+             backward of step i - 1, so that it runs while exchange i - 1 is on the wire
   e2e        same metric through lp_render_step_host with pinned HOST buffers (H2D + D2H inside), on
              every rank at once, aggregated
   roofline   dominant kernel: algorithmic bytes per launch / its mean CUDA-event duration (an
@@ -22,6 +26,10 @@ the default run also appends the configs[2] strong-scaling measurement as ``stro
   cpu_baseline  the oracle (reference glue mirror over the torch kaolin restatement) on the host cores
 
 ``--impl reference`` times that CPU path alone and prints the same line with "impl": "reference".
+``--workload c5`` is BASELINE.json configs[4] (tools/train_step.py: renderer + stand-in UNet + exchange + fused Adam).
+Experiment switches (environment): LP_RASTER_CTAS, LP_WALK_CTAS, LP_EXCHANGE_CTAS, LP_EXCHANGE_BULK, LP_PDL,
+LP_GATE_RASTER, LP_RASTER_LOOKAHEAD, LP_PREP_AFTER_BWD, LP_MICRO, LP_PIPE_STEPS, LP_B200_LIB (another build of the
+library, e.g. the -DLP_CHECKED one: its violation counter is reported), LP_DEBUG_CHECK.
 """
 import argparse
 import ctypes

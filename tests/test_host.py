@@ -47,6 +47,24 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     assert int(out[4]) == _lib.LpBackwardArgs.workspace_bytes.offset
 
 
+def test_python_constants_match_the_header(tmp_path):
+    """Flags, options, interpolation modes and the exchange structs of ``_lib.py`` against ``include/lp_b200.h`` (a C
+    program prints the header's values)."""
+    names = [n for n in dir(_lib) if re.fullmatch(r"LP_(FLAG|OPT|INTERP|ERR)_[A-Z0-9_]+|LP_OK|LP_EXCHANGE_FLAG_BYTES", n)]
+    assert {"LP_OPT_WALK_CTAS_PER_SM", "LP_OPT_EXCHANGE_BULK", "LP_FLAG_GRAD_INTERLEAVED", "LP_FLAG_MICRO_ON"} <= set(names)
+    body = "".join(f'printf("{n} %lld\\n", (long long)({n}));' for n in names)
+    body += 'printf("sizeof_LpExchangeArgs %zu\\n", sizeof(LpExchangeArgs));printf("sizeof_LpAdamArgs %zu\\n", sizeof(LpAdamArgs));'
+    prog = tmp_path / "consts.c"
+    prog.write_text('#include <stdio.h>\n#include "lp_b200.h"\nint main(){' + body + 'return 0;}\n')
+    exe = tmp_path / "consts"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for n in names:
+        assert int(out[n]) == int(getattr(_lib, n)), n
+    assert int(out["sizeof_LpExchangeArgs"]) == ctypes.sizeof(_lib.LpExchangeArgs)
+    assert int(out["sizeof_LpAdamArgs"]) == ctypes.sizeof(_lib.LpAdamArgs)
+
+
 def test_argument_validation_without_a_gpu():
     """Bad arguments are rejected before any CUDA call is made."""
     L = _lib.lib()
