@@ -168,8 +168,9 @@ typedef struct LpBackwardArgs {
     uint64_t       workspace_bytes;
     const float   *under_mask;     /* optional (B,1,H,W), face-feature path: grad_image is dL/d composed and is scaled
                                       by (1 - under_mask) per pixel (the backward of the fused composition) */
-    /* optional (both or none; LP_FLAG_MASK_IMAGE): the forward call's list of live footprints, from
-       lp_forward_worklist(), valid while that call's workspace has not been reused.  The backward then visits the
+    /* optional (both or none; LP_FLAG_MASK_IMAGE): the forward call's list of covered footprints (8 x 4 pixels that hold
+       at least one covered pixel, written by the footprint kernel) and the control block holding its length, from
+       lp_forward_worklist(); valid while that call's workspace has not been reused.  The backward then visits the
        listed footprints directly instead of scanning the coverage flags of all of them */
     const void    *worklist;
     const void    *worklist_ctrl;
@@ -213,7 +214,8 @@ int lp_cameras_from_views(const float *elev, const float *azim, const float *rad
                           float look_at_height, int32_t B, float *cameras, void *stream);
 
 uint64_t    lp_backward_workspace_bytes(int32_t C, int32_t Th, int32_t Tw);
-/* where in `args->workspace` the forward leaves its live-footprint list (for LpBackwardArgs.worklist / worklist_ctrl) */
+/* where in `args->workspace` the forward leaves its covered-footprint list and its control block (for
+ * LpBackwardArgs.worklist / worklist_ctrl) */
 int lp_forward_worklist(const LpForwardArgs *args, const void **worklist, const void **worklist_ctrl);
 
 int lp_render_forward(const LpForwardArgs *args, void *stream);
