@@ -28,7 +28,7 @@ the default run also appends the configs[2] strong-scaling measurement as ``stro
 ``--impl reference`` times that CPU path alone and prints the same line with "impl": "reference".
 ``--workload c5`` is BASELINE.json configs[4] (tools/train_step.py: renderer + stand-in UNet + exchange + fused Adam).
 Experiment switches (environment): LP_RASTER_CTAS, LP_WALK_CTAS, LP_EXCHANGE_CTAS, LP_EXCHANGE_BULK, LP_PDL,
-LP_GATE_RASTER, LP_RASTER_LOOKAHEAD, LP_PREP_AFTER_BWD, LP_MICRO, LP_PIPE_STEPS, LP_B200_LIB (another build of the
+LP_GATE_RASTER, LP_RASTER_LOOKAHEAD, LP_PREP_AFTER_BWD, LP_CLEAR_ASIDE, LP_MICRO, LP_PIPE_STEPS, LP_B200_LIB (another build of the
 library, e.g. the -DLP_CHECKED one: its violation counter is reported), LP_DEBUG_CHECK.
 """
 import argparse
@@ -236,10 +236,17 @@ class DeviceStep:
         _lib.check(L.lp_render_raster(ctypes.byref(self.fwd), stream))
         self.launches_prepare += L.lp_last_launch_count()
 
-    def shade_backward(self, stream, torch_stream, with_raster):
+    def shade_backward(self, stream, torch_stream, with_raster, aux=None):
         """The rest of the step: (tile rasterizer fused with the texture fetch | texture fetch only), then
-        zero the gradient and scatter the upstream gradient into it."""
+        zero the gradient and scatter the upstream gradient into it.  ``aux`` (a torch stream): the accumulation
+        buffer is cleared there, NEXT TO the texture fetch instead of between it and the backward (the clear of 16.8 MB is
+        otherwise a link of the step's critical chain); the backward is then told not to clear it again."""
         L = _lib.lib()
+        aside = aux is not None and self.accum.numel() > 0 and bool(self.bwd.workspace)
+        if aside:
+            aux.wait_stream(torch_stream)                 # everything that still uses the buffer precedes the clear
+            with torch.cuda.stream(aux):
+                self.accum.zero_()
         if with_raster:
             _lib.check(L.lp_render_shade(ctypes.byref(self.fwd), stream))
         else:
@@ -248,7 +255,12 @@ class DeviceStep:
         if not self.accum.numel():
             with torch.cuda.stream(torch_stream):
                 self.grad_tex.zero_()
+        flags = self.bwd.flags
+        if aside:
+            torch_stream.wait_stream(aux)
+            self.bwd.flags = flags | _lib.LP_FLAG_GRAD_NO_CLEAR
         _lib.check(L.lp_render_backward(ctypes.byref(self.bwd), stream))
+        self.bwd.flags = flags
         self.launches = self.launches_prepare + n + L.lp_last_launch_count()
 
     def run_split(self, stream=None):
@@ -553,6 +565,10 @@ def measure(args, env, w, full):
     # the SMs with it (LP_GATE_RASTER=0: free-running)
     gate_raster = world > 1 and os.environ.get("LP_GATE_RASTER", "1") == "1"
     gate_prep = world > 1 and os.environ.get("LP_GATE_PREP", "0") == "1"       # the same for geometry + bins of step k + 2 (measured worse: 134 vs 109 us at 4 GPUs)
+    # LP_CLEAR_ASIDE=1: the backward's accumulation buffer is cleared on a fourth stream next to the texture fetch instead
+    # of by lp_render_backward itself between the fetch and the scatter (LP_FLAG_GRAD_NO_CLEAR).  Measured slower on
+    # config 2 (65.4 / 65.7 vs 63.1 / 63.1 us per step: the clear then competes with the fetch), so it is off by default
+    clear_stream = torch.cuda.Stream(device, priority=-1) if pipeline and os.environ.get("LP_CLEAR_ASIDE", "0") == "1" else None
     h_prep = ctypes.c_void_p(prep_stream.cuda_stream) if pipeline else None
     h_rast = ctypes.c_void_p(rast_stream.cuda_stream) if pipe_deep else None
     h_main = ctypes.c_void_p(stream.cuda_stream)
@@ -606,7 +622,7 @@ def measure(args, env, w, full):
             issue_front((i + 1) % len(sets))             # gated on the backward of step i - 1 (pipe_state["prev"])
         pipe_state["front"][k] = False
         stream.wait_event(prep_done[k])
-        sets[k].shade_backward(h_main, stream, pipe_raster)
+        sets[k].shade_backward(h_main, stream, pipe_raster, aux=clear_stream)
         bwd_done[k].record(stream)
         pipe_state["prev"] = k
         if with_exchange:

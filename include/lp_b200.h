@@ -79,6 +79,9 @@ enum {
     LP_FLAG_PLAIN_EPS        = 1u << 8,  /* s += eps instead of s += copysign(eps, s) */
     LP_FLAG_AFFINE_INTERP    = 1u << 9,  /* screen-space interpolation: z0 = sum w_k z_k, w'_k = w_k, instead of perspective-correct */
     LP_FLAG_SH_BAND1_XZY     = 1u << 10, /* SH band-1 axis order (x, z, y) instead of (y, z, x) */
+    LP_FLAG_GRAD_NO_CLEAR    = 1u << 11, /* lp_render_backward with a workspace: the caller has already zeroed the first
+                                            Th * Tw * 16 bytes of the workspace (e.g. on another stream, next to the texture
+                                            fetch), so the call does not clear it again */
     LP_FLAG_MICRO_OFF        = 1u << 22, /* never / always rasterize small faces face-parallel in the setup kernel */
     LP_FLAG_MICRO_ON         = 1u << 23  /* (default: on when the mesh has at least one face per 16 pixels) */
     /* bits 24-30: stop-after-stage ablation switches, compiled in only with -DLP_PROFILE (tools/), ignored otherwise */

@@ -34,6 +34,7 @@ LP_FLAG_BBOX_HALF_OPEN = 1 << 7
 LP_FLAG_PLAIN_EPS = 1 << 8
 LP_FLAG_AFFINE_INTERP = 1 << 9
 LP_FLAG_SH_BAND1_XZY = 1 << 10
+LP_FLAG_GRAD_NO_CLEAR = 1 << 11
 LP_FLAG_MICRO_OFF = 1 << 22
 LP_FLAG_MICRO_ON = 1 << 23
 LP_OPT_PDL = 1

@@ -103,6 +103,49 @@ def test_config2_benched_step_vs_oracle(exchange_form):
         assert_close(p_gpu.cpu()[solid], p_ref.detach()[solid], "texture after one fused Adam step from the interleaved gradient", rtol=1e-5, atol=1e-6)
 
 
+def test_accumulation_buffer_cleared_next_to_the_texture_fetch():
+    """bench.py's pipelined step clears the backward's accumulation buffer on another stream, next to the texture fetch,
+    and passes LP_FLAG_GRAD_NO_CLEAR: same gradient as the call that clears the buffer itself, from eager launches and
+    from a CUDA graph (the fork / join of the clear is captured); and the flag alone really skips the clear (a second
+    backward accumulates on top of the first)."""
+    from bench import WORKLOADS, DeviceStep, workload_cameras
+    w = dict(WORKLOADS["c2"], B=3, H=160, W=208, T=256)
+    verts, faces, uv = scene(w["shape"], w["scale"], w["dy"])
+    dev = torch.device(DEV)
+    geom = _geom(verts, faces, uv)
+    ref = DeviceStep(geom, w, workload_cameras(w, w["B"], 4), 1, dev, grad_layout="interleaved")
+    st = DeviceStep(geom, w, workload_cameras(w, w["B"], 4), 1, dev, grad_layout="interleaved")
+    main, aux = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    h = ctypes.c_void_p(main.cuda_stream)
+    ref.run_split()
+    torch.cuda.synchronize()
+    g_ref = ref.gradient().clone()
+    assert float(g_ref.abs().sum()) > 0
+    with torch.cuda.stream(main):
+        st.accum.fill_(77)                               # whatever a previous step left behind
+        st.prepare(h, True)
+        st.shade_backward(h, main, True, aux=aux)
+    torch.cuda.synchronize()
+    assert_close(st.gradient(), g_ref, "gradient with the buffer cleared on the side stream")
+    assert torch.equal(st.image, ref.image)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(main):
+        with torch.cuda.graph(g, stream=main):
+            st.prepare(h, True)
+            st.shade_backward(h, main, True, aux=aux)
+        st.accum.fill_(5)
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    assert_close(st.gradient(), g_ref, "gradient from the captured fork / clear / join")
+    # the flag alone: no clear, so a second backward adds to the first
+    st.bwd.flags |= _lib.LP_FLAG_GRAD_NO_CLEAR
+    with torch.cuda.stream(main):
+        _lib.check(_lib.lib().lp_render_backward(ctypes.byref(st.bwd), h))
+    torch.cuda.synchronize()
+    assert_close(st.gradient(), 2 * g_ref, "two backwards without a clear in between", rtol=1e-4, atol=2e-5)
+
+
 def test_config2_visibility_buffers_vs_oracle():
     """face_idx, depth and barycentric weights of configs[1] (B = 8 in one call) against the oracle's buffers:
     same fp32 expression tree in the same order, so all three are compared bit for bit."""
