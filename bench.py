@@ -937,6 +937,11 @@ def main():
     # with two, 85.8 with three, 86.8 with four).  LP_RASTER_CTAS / LP_PDL override (experiments).
     if args.pipeline != "off":
         _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_RASTER_CTAS_PER_SM, 2))
+        if env.world == 1:
+            # ... and four instead of eight CTAs per SM for the texture fetch and the backward (config 2, four A/B pairs:
+            # 61.8-62.5 vs 62.7-63.8 us per step); at N > 1, where that chain is followed by the exchange, the
+            # library's default stays
+            _lib.check(_lib.lib().lp_set_option(_lib.LP_OPT_WALK_CTAS_PER_SM, 4))
     for name, opt in (("LP_PDL", _lib.LP_OPT_PDL), ("LP_RASTER_CTAS", _lib.LP_OPT_RASTER_CTAS_PER_SM),
                       ("LP_EXCHANGE_CTAS", _lib.LP_OPT_EXCHANGE_CTAS), ("LP_WALK_CTAS", _lib.LP_OPT_WALK_CTAS_PER_SM),
                       ("LP_EXCHANGE_BULK", _lib.LP_OPT_EXCHANGE_BULK)):
